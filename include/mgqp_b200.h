@@ -1,0 +1,127 @@
+/* mgqp_b200.h -- C ABI of the B200-native batched dense QP engine for the mgqp hot path.
+ *
+ * The reference (erreur404/Motion-generation-using-quadratic-programs) solves every QP of its
+ * control cycle through ONE call (src/mgqp.cpp:708 and :725):
+ *
+ *     double solve_quadprog(Matrix<double>& G, Vector<double>& g0,
+ *                           const Matrix<double>& CE, const Vector<double>& ce0,
+ *                           const Matrix<double>& CI, const Vector<double>& ci0,
+ *                           Vector<double>& x);          // include/QuadProgpp/QuadProg++.hh:69-72
+ *
+ * implemented by the prebuilt lib/QuadProgpp/libquadprog.a (Goldfarb-Idnani dual active set,
+ * fp64).  This library replaces that path:
+ *
+ *   - include/QuadProgpp/QuadProg++.hh + libmgqp_b200.so export the SAME C++ symbol
+ *     (_Z14solve_quadprogRN7ArrayHH6MatrixIdEERNS_6VectorIdEERKS1_RKS4_S7_S9_S5_), so
+ *     src/mgqp.cpp links unchanged;
+ *   - the entry points below are the batched form the reference's FFI for this path would bind.
+ *
+ * Problem (QuadProg++.hh:8-13):   min 1/2 x'Gx + g0'x   s.t.  CE'x + ce0 = 0,  CI'x + ci0 >= 0
+ * Orientation (QuadProg++.hh:15-25): G n*n, CE n*p, CI n*m, row-major, ONE CONSTRAINT PER COLUMN.
+ *
+ * Everything is plain pointers and sizes; no C++ or torch types cross this boundary.
+ */
+#ifndef MGQP_B200_H
+#define MGQP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-QP verdicts.  0/1 are the two outcomes the reference RETURNS (cost, or +inf:
+ * QuadProg++.hh:27-29, tested by the caller at src/mgqp.cpp:717); 2/3 are the two it THROWS
+ * (std::logic_error from cholesky_decomposition, std::runtime_error "Constraints are linearly
+ * dependent"); 4 does not exist in the reference, which has no iteration limit and can spin
+ * forever after a degenerate add_constraint (note N3). */
+enum {
+  MGQP_STATUS_OK = 0,
+  MGQP_STATUS_INFEASIBLE = 1,   /* f = +inf, x = last iterate (as the reference leaves it)    */
+  MGQP_STATUS_NOT_PD = 2,       /* f = the non-positive Cholesky pivot (for the error message) */
+  MGQP_STATUS_EQ_DEPENDENT = 3, /* f, x = state when the dependent equality was met            */
+  MGQP_STATUS_ITER_CAP = 4
+};
+
+/* Return codes of the entry points themselves (argument / CUDA errors; never a per-QP verdict). */
+enum {
+  MGQP_OK = 0,
+  MGQP_ERR_INVALID_ARG = -1,
+  MGQP_ERR_UNSUPPORTED_SHAPE = -2,
+  MGQP_ERR_CUDA = -3,
+  MGQP_ERR_NO_DEVICE = -4
+};
+
+/* flags */
+enum {
+  MGQP_FLAG_DEFAULT = 0,
+  /* Allow fused multiply-add and tree reductions.  Faster, but x/f are then only within ~1e-12 of
+   * the reference instead of bit-identical, and a decision that sits exactly on a tie can differ.
+   * Off by default: the default path reproduces the reference's arithmetic operation by operation. */
+  MGQP_FLAG_FAST_MATH = 1,
+  /* Stage inputs with plain coalesced loads instead of TMA bulk copies (debug / odd alignments). */
+  MGQP_FLAG_NO_BULK_COPY = 2,
+  /* Static round-robin tile assignment instead of the persistent atomic work queue. */
+  MGQP_FLAG_STATIC_SCHEDULE = 4
+};
+
+/* One batch of `batch` independent QPs of one shape, field-wise SoA, DEVICE pointers.
+ * Field k of QP b starts at  ptr + b * stride  (stride in ELEMENTS; 0 broadcasts one instance to
+ * the whole batch; the natural stride -- n*n, n, n*p, p, n*m, m -- enables the TMA staging path).
+ * Within a QP the layout is exactly QuadProg++'s row-major Matrix storage (Array.hh:910-919), so
+ * B = 1 is a plain copy of Matrix::v[0]. */
+typedef struct mgqp_batch {
+  int32_t n, p, m;
+  int64_t batch;
+  const double *G, *g0, *CE, *ce0, *CI, *ci0; /* inputs are never modified                       */
+  int64_t sG, sg0, sCE, sce0, sCI, sci0;
+  double* x;       /* [batch][n]                                                              */
+  double* f;       /* [batch]    cost, +inf if infeasible                                     */
+  int32_t* status; /* [batch]    MGQP_STATUS_*                                                */
+  int32_t* iq;     /* [batch]    size of the final active set (equalities included); or NULL  */
+  int32_t* A;      /* [batch][p+m] active set in the solver's encoding: equality i -> -(i+1),
+                      inequality i -> i; first iq[b] entries valid, rest 0x7fffffff; or NULL   */
+  int32_t* iters;  /* [batch]    number of step-direction computations (l2a passes); or NULL  */
+  int32_t max_iter; /* <= 0: default 100 + 10*(p+m)                                            */
+  int32_t flags;    /* MGQP_FLAG_*                                                              */
+} mgqp_batch;
+
+/* Solve a device-resident batch on `device`, asynchronously on `stream` (a cudaStream_t passed
+ * as void*; NULL = the legacy default stream).  Thread-safe; no global mutable state apart from a
+ * per-device ring of work-queue counters.  Replaces QuadProg++.hh:69-72 for batches. */
+int solve_quadprog_batched(const mgqp_batch* d, int device, void* stream);
+
+/* Same, but every pointer in `h` is a HOST pointer (pinned or pageable).  The call uploads the
+ * inputs in chunks, solves, downloads x/f/status(/iq/A/iters) and returns when the results are in
+ * host memory; copies overlap compute through two streams.  This is the "plugin call with host
+ * buffers" that bench.py times as e2e.  chunk <= 0 picks a default. */
+int solve_quadprog_batched_host(const mgqp_batch* h, int device, int64_t chunk);
+
+/* Host buffers, sharded by QP index over `ndev` devices (devices[0..ndev-1]) with one host thread
+ * and its own streams per device, chunks handed out from a shared atomic counter
+ * (no collective, the QPs are independent). */
+int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int ndev, int64_t chunk);
+
+/* Single QP with host pointers in QuadProg++ layout; what the C++ drop-in solve_quadprog() calls.
+ * G_factor (optional, n*n) receives the Cholesky factor the reference leaves in G
+ * (QuadProg++.hh:42-45).  Returns MGQP_OK and the verdict through *status. */
+int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const double* g0,
+                   const double* CE, const double* ce0, const double* CI, const double* ci0,
+                   double* x, double* f, int32_t* status, double* G_factor, int device);
+
+/* Introspection. */
+const char* mgqp_status_string(int status);
+const char* mgqp_last_error(void);        /* thread-local text of the last non-OK return        */
+int mgqp_device_count(void);
+/* Kernel launches issued by this library in this process (all threads); for bench bookkeeping. */
+int64_t mgqp_kernel_launch_count(void);
+/* Which kernel family a shape maps to: 8/16/32 = lanes per QP of the warp kernel, 0 = CTA-per-QP
+ * kernel, <0 = unsupported.  smem_bytes_per_cta / ctas_per_sm (optional) receive the launch plan. */
+int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int32_t* warps_per_cta);
+/* Compulsory HBM bytes per QP for a shape (every input once, x/f/status once); SURVEY.md 8(d). */
+int64_t mgqp_algorithmic_bytes(int32_t n, int32_t p, int32_t m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGQP_B200_H */

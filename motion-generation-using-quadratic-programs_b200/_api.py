@@ -1,0 +1,305 @@
+"""Host-side binding of the C ABI in include/mgqp_b200.h.
+
+The names and argument meaning mirror the reference boundary
+(include/QuadProgpp/QuadProg++.hh:69-72, called from src/mgqp.cpp:708/:725):
+
+    f = solve_quadprog(G, g0, CE, ce0, CI, ci0, x)
+
+``G`` n*n, ``CE`` n*p, ``CI`` n*m with one constraint per COLUMN; returns the cost, ``inf`` when
+infeasible; raises :class:`LogicError` (the reference throws ``std::logic_error``) for dimension
+mismatches and a non-positive-definite ``G`` and :class:`RuntimeError` ("Constraints are linearly
+dependent") like the reference's ``std::runtime_error``.  ``G`` is overwritten by its Cholesky
+factor (QuadProg++.hh:42-45).
+
+There is NO CPU fallback: everything here calls ``libmgqp_b200.so`` (hand-written sm_100a CUDA);
+if the library is missing the import of the solver entry points fails loudly.  torch is used only
+for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+__all__ = [
+    "LogicError", "QPResult", "STATUS", "lib", "lib_path", "solve_quadprog", "solve_quadprog_batched",
+    "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
+    "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "mgqp_batch",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FLAG_FAST_MATH = 1
+FLAG_NO_BULK_COPY = 2
+FLAG_STATIC_SCHEDULE = 4
+STATUS = {0: "ok", 1: "infeasible", 2: "not_pd", 3: "eq_dependent", 4: "iter_cap"}
+
+
+class LogicError(ValueError):
+    """What the reference reports as std::logic_error."""
+
+
+class mgqp_batch(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("p", C.c_int32), ("m", C.c_int32), ("batch", C.c_int64),
+        ("G", C.c_void_p), ("g0", C.c_void_p), ("CE", C.c_void_p), ("ce0", C.c_void_p),
+        ("CI", C.c_void_p), ("ci0", C.c_void_p),
+        ("sG", C.c_int64), ("sg0", C.c_int64), ("sCE", C.c_int64), ("sce0", C.c_int64),
+        ("sCI", C.c_int64), ("sci0", C.c_int64),
+        ("x", C.c_void_p), ("f", C.c_void_p), ("status", C.c_void_p), ("iq", C.c_void_p),
+        ("A", C.c_void_p), ("iters", C.c_void_p),
+        ("max_iter", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+class QPResult(NamedTuple):
+    x: object
+    f: object
+    status: object
+    iq: object = None
+    A: object = None
+    iters: object = None
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libmgqp_b200.so")
+
+
+def lib():
+    """The CUDA library.  Raises if it has not been built (``python __graft_entry__.py``)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "mgqp_b200 has no CPU fallback.")
+        L = C.CDLL(path)
+        L.solve_quadprog_batched.restype = C.c_int
+        L.solve_quadprog_batched.argtypes = [C.POINTER(mgqp_batch), C.c_int, C.c_void_p]
+        L.solve_quadprog_batched_host.restype = C.c_int
+        L.solve_quadprog_batched_host.argtypes = [C.POINTER(mgqp_batch), C.c_int, C.c_int64]
+        L.solve_quadprog_batched_multi.restype = C.c_int
+        L.solve_quadprog_batched_multi.argtypes = [C.POINTER(mgqp_batch), C.POINTER(C.c_int), C.c_int, C.c_int64]
+        L.mgqp_solve_one.restype = C.c_int
+        L.mgqp_solve_one.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 6 + [C.c_void_p, C.POINTER(C.c_double),
+                                                                           C.POINTER(C.c_int32), C.c_void_p, C.c_int]
+        L.mgqp_status_string.restype = C.c_char_p
+        L.mgqp_status_string.argtypes = [C.c_int]
+        L.mgqp_last_error.restype = C.c_char_p
+        L.mgqp_device_count.restype = C.c_int
+        L.mgqp_kernel_launch_count.restype = C.c_int64
+        L.mgqp_plan.restype = C.c_int
+        L.mgqp_plan.argtypes = [C.c_int32] * 3 + [C.POINTER(C.c_int32)] * 2
+        L.mgqp_algorithmic_bytes.restype = C.c_int64
+        L.mgqp_algorithmic_bytes.argtypes = [C.c_int32] * 3
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = lib().mgqp_last_error().decode()
+        if rc == -1:
+            raise ValueError(f"mgqp_b200: invalid argument: {msg}")
+        if rc == -2:
+            raise NotImplementedError(f"mgqp_b200: {msg}")
+        raise RuntimeError(f"mgqp_b200: error {rc}: {msg}")
+
+
+def plan(n: int, p: int, m: int):
+    """(lanes per QP, warps per CTA, dynamic smem bytes per CTA) the launcher would use."""
+    smem, warps = C.c_int32(0), C.c_int32(0)
+    gw = lib().mgqp_plan(n, p, m, C.byref(smem), C.byref(warps))
+    return gw, warps.value, smem.value
+
+
+def algorithmic_bytes(n: int, p: int, m: int) -> int:
+    return int(lib().mgqp_algorithmic_bytes(n, p, m))
+
+
+def kernel_launch_count() -> int:
+    return int(lib().mgqp_kernel_launch_count())
+
+
+# ------------------------------------------------------------------ device-resident batches
+def _stride(t, natural: int) -> int:
+    """Element stride between QPs of a [B, ...] tensor (0 for an un-batched, broadcast field)."""
+    if t.shape[0] == 1 and natural > 0 and t.stride(0) != natural:
+        return 0
+    return t.stride(0)
+
+
+def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = False, max_iter: int = 0,
+                           flags: int = 0, stream=None, out: Optional[QPResult] = None) -> QPResult:
+    """Solve a batch of QPs held in CUDA tensors (float64).
+
+    Shapes: ``G [B,n,n]``, ``g0 [B,n]``, ``CE [B,n,p]``, ``ce0 [B,p]``, ``CI [B,n,m]``, ``ci0 [B,m]``;
+    a leading dimension of 1 broadcasts that field to the whole batch.  Asynchronous on ``stream``
+    (default: torch's current stream).  Returns torch tensors on the same device.
+    """
+    import torch
+
+    if not G.is_cuda:
+        raise ValueError("solve_quadprog_batched takes CUDA tensors; use solve_quadprog_batched_host for host arrays")
+    dev = G.device
+    n = G.shape[-1]
+    p = ce0.shape[-1]
+    m = ci0.shape[-1]
+    B = max(t.shape[0] for t in (G, g0, CE, ce0, CI, ci0))
+    _validate_shapes(n, p, m, tuple(G.shape[1:]), tuple(g0.shape[1:]), tuple(CE.shape[1:]), tuple(ce0.shape[1:]),
+                     tuple(CI.shape[1:]), tuple(ci0.shape[1:]))
+    ts = []
+    for t in (G, g0, CE, ce0, CI, ci0):
+        if t.dtype != torch.float64:
+            raise ValueError("all inputs must be float64")
+        if t.shape[0] not in (1, B):
+            raise ValueError("leading dimensions must be B or 1")
+        ts.append(t if t[0].is_contiguous() or t.numel() == 0 else t.contiguous())
+    G, g0, CE, ce0, CI, ci0 = ts
+    if out is None:
+        x = torch.empty((B, n), dtype=torch.float64, device=dev)
+        f = torch.empty((B,), dtype=torch.float64, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        iq = A = iters = None
+        if want_active_set:
+            iq = torch.empty((B,), dtype=torch.int32, device=dev)
+            A = torch.empty((B, p + m), dtype=torch.int32, device=dev)
+            iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        out = QPResult(x, f, status, iq, A, iters)
+    d = mgqp_batch()
+    d.n, d.p, d.m, d.batch = n, p, m, B
+    nat = (n * n, n, n * p, p, n * m, m)
+    for name, t, na in zip(("G", "g0", "CE", "ce0", "CI", "ci0"), ts, nat):
+        setattr(d, name, t.data_ptr() if t.numel() else out.x.data_ptr())
+        setattr(d, "s" + name, (0 if t.shape[0] == 1 and B > 1 else (t.stride(0) if na else 0)))
+    d.x, d.f, d.status = out.x.data_ptr(), out.f.data_ptr(), out.status.data_ptr()
+    d.iq = out.iq.data_ptr() if out.iq is not None else None
+    d.A = out.A.data_ptr() if out.A is not None else None
+    d.iters = out.iters.data_ptr() if out.iters is not None else None
+    d.max_iter, d.flags = max_iter, flags
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+    _check(lib().solve_quadprog_batched(C.byref(d), dev.index if dev.index is not None else 0, C.c_void_p(sptr)))
+    return out
+
+
+# ------------------------------------------------------------------ host buffers
+def _host_desc(G, g0, CE, ce0, CI, ci0, want_active_set, max_iter, flags, outs=None):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (G, g0, CE, ce0, CI, ci0)]
+    G, g0, CE, ce0, CI, ci0 = arrs
+    B, n = g0.shape
+    p = ce0.shape[1]
+    m = ci0.shape[1]
+    _validate_shapes(n, p, m, G.shape[1:], g0.shape[1:], CE.shape[1:], ce0.shape[1:], CI.shape[1:], ci0.shape[1:])
+    if outs is None:
+        x = np.empty((B, n))
+        f = np.empty(B)
+        status = np.empty(B, dtype=np.int32)
+        iq = A = iters = None
+        if want_active_set:
+            iq = np.empty(B, dtype=np.int32)
+            A = np.empty((B, p + m), dtype=np.int32)
+            iters = np.empty(B, dtype=np.int32)
+        outs = QPResult(x, f, status, iq, A, iters)
+    d = mgqp_batch()
+    d.n, d.p, d.m, d.batch = n, p, m, B
+    nat = (n * n, n, n * p, p, n * m, m)
+    dummy = outs.x
+    for name, a, na in zip(("G", "g0", "CE", "ce0", "CI", "ci0"), arrs, nat):
+        setattr(d, name, a.ctypes.data if a.size else dummy.ctypes.data)
+        setattr(d, "s" + name, na)
+    d.x, d.f, d.status = outs.x.ctypes.data, outs.f.ctypes.data, outs.status.ctypes.data
+    d.iq = outs.iq.ctypes.data if outs.iq is not None else None
+    d.A = outs.A.ctypes.data if outs.A is not None else None
+    d.iters = outs.iters.ctypes.data if outs.iters is not None else None
+    d.max_iter, d.flags = max_iter, flags
+    return d, outs, arrs
+
+
+def solve_quadprog_batched_host(G, g0, CE, ce0, CI, ci0, *, want_active_set=False, max_iter=0, flags=0,
+                                device: int = 0, chunk: int = 0, out: Optional[QPResult] = None) -> QPResult:
+    """Host (numpy) arrays in, numpy arrays out; H2D / solve / D2H pipelined inside the library."""
+    d, outs, keep = _host_desc(G, g0, CE, ce0, CI, ci0, want_active_set, max_iter, flags, out)
+    _check(lib().solve_quadprog_batched_host(C.byref(d), device, chunk))
+    return outs
+
+
+def solve_quadprog_batched_multi(G, g0, CE, ce0, CI, ci0, *, devices, want_active_set=False, max_iter=0, flags=0,
+                                 chunk: int = 0, out: Optional[QPResult] = None) -> QPResult:
+    """Host arrays sharded by QP index over several GPUs, one host thread per device (no collective)."""
+    d, outs, keep = _host_desc(G, g0, CE, ce0, CI, ci0, want_active_set, max_iter, flags, out)
+    devs = (C.c_int * len(devices))(*devices)
+    _check(lib().solve_quadprog_batched_multi(C.byref(d), devs, len(devices), chunk))
+    return outs
+
+
+# ------------------------------------------------------------------ the reference's own call
+def _validate_shapes(n, p, m, sG, sg0, sCE, sce0, sCI, sci0):
+    """The five dimension checks of solve_quadprog, with the reference's exception texts
+    (.rodata of QuadProg++.o)."""
+    sG, sCE, sCI = tuple(sG), tuple(sCE), tuple(sCI)
+    if sG[0] != sG[1]:
+        raise LogicError(f"The matrix G is not a squared matrix ({sG[0]} x {sG[1]})")
+    if sCE[0] != n:
+        raise LogicError(f"The matrix CE is incompatible (incorrect number of rows {sCE[0]} , expecting {n})")
+    if tuple(sce0)[0] != sCE[1]:
+        raise LogicError(f"The vector ce0 is incompatible (incorrect dimension {tuple(sce0)[0]}, expecting {sCE[1]})")
+    if sCI[0] != n:
+        raise LogicError(f"The matrix CI is incompatible (incorrect number of rows {sCI[0]} , expecting {n})")
+    if tuple(sci0)[0] != sCI[1]:
+        raise LogicError(f"The vector ci0 is incompatible (incorrect dimension {tuple(sci0)[0]}, expecting {sCI[1]})")
+
+
+def _fmt_double(v: float) -> str:
+    """std::ostream << double with default precision (6 significant digits, %g)."""
+    return "%g" % v
+
+
+def solve_quadprog(G, g0, CE, ce0, CI, ci0, x=None, *, device: int = 0) -> float:
+    """Single QP, reference semantics (QuadProg++.hh:69-72).
+
+    ``G`` (float64 ndarray, n*n) is overwritten by its Cholesky factor; ``x`` (optional float64
+    ndarray of length n) receives the solution, which is also available as ``solve_quadprog.x``
+    of the call through the returned value's companion: use ``solve_quadprog_x`` if you need both.
+    Returns the cost, ``math.inf`` if infeasible.
+    """
+    G_arr = np.asarray(G)
+    g0 = np.ascontiguousarray(g0, dtype=np.float64)
+    n = G_arr.shape[1] if G_arr.ndim == 2 else 0
+    CE = np.ascontiguousarray(CE, dtype=np.float64)
+    CI = np.ascontiguousarray(CI, dtype=np.float64)
+    if G_arr.ndim != 2 or CE.ndim != 2 or CI.ndim != 2:
+        raise LogicError("G, CE and CI must be 2-D (n*n, n*p, n*m; use shape (n, 0) for an empty block)")
+    ce0 = np.ascontiguousarray(ce0, dtype=np.float64).reshape(-1)
+    ci0 = np.ascontiguousarray(ci0, dtype=np.float64).reshape(-1)
+    _validate_shapes(n, CE.shape[1], CI.shape[1], G_arr.shape, g0.shape, CE.shape, ce0.shape, CI.shape, ci0.shape)
+    Gc = np.ascontiguousarray(G_arr, dtype=np.float64)
+    p, m = CE.shape[1], CI.shape[1]
+    xs = np.zeros(n)
+    f = C.c_double(0.0)
+    st = C.c_int32(0)
+    Gf = np.empty((n, n))
+    _check(lib().mgqp_solve_one(n, p, m, Gc.ctypes.data, g0.ctypes.data, CE.ctypes.data if CE.size else None,
+                                ce0.ctypes.data if ce0.size else None, CI.ctypes.data if CI.size else None,
+                                ci0.ctypes.data if ci0.size else None, xs.ctypes.data, C.byref(f), C.byref(st),
+                                Gf.ctypes.data, device))
+    if st.value == 2:
+        raise LogicError("Error in cholesky decomposition, sum: " + _fmt_double(f.value))
+    if isinstance(G, np.ndarray) and G.dtype == np.float64:
+        G[...] = Gf  # "The matrix G is modified within the function" (QuadProg++.hh:42-45)
+    if x is not None:
+        x[...] = xs
+    solve_quadprog.last_x = xs
+    solve_quadprog.last_status = st.value
+    if st.value == 3:
+        raise RuntimeError("Constraints are linearly dependent")
+    if st.value == 1:
+        return math.inf
+    return f.value

@@ -1,0 +1,150 @@
+// Persistent warp-per-tile kernel around gi_solve_tile (n <= 32).
+//
+// Every WARP is an independent worker: it pulls a tile of 32/GW consecutive QPs from an atomic work
+// queue, stages the tile's six input fields into its private shared-memory block with TMA bulk
+// copies (cp.async.bulk, one per field, completion on the warp's own mbarrier), prefetches the
+// NEXT tile into L2 while it solves the current one, and writes x/f/status straight to HBM.
+// There is no __syncthreads anywhere; a CTA is just a bag of warps sized to fill the SM's shared
+// memory, and the grid is one resident wave (148 SMs x CTAs/SM).
+#pragma once
+#include "gi_small.cuh"
+
+namespace mgqp {
+
+struct SmallParams {
+  TileView tv;
+  long long batch, tiles;
+  const double* in[6];   // G, g0, CE, ce0, CI, ci0
+  long long stride[6];   // element stride between QPs
+  int size[6];           // elements per QP: n*n, n, n*p, p, n*m, m
+  int off[6];            // offsets of the fields inside the warp block (doubles)
+  unsigned bulk_mask;    // bit k: field k may be staged with one bulk copy per full tile
+  unsigned bulk_bytes;   // sum of bytes of the bulk-staged fields of one full tile
+  double* x; double* f; int* status; int* iq; int* A; int* iters;
+  int max_iter;
+  unsigned* ticket;      // work-queue head (zeroed before launch); nullptr = static round robin
+  int bar_bytes;         // bytes reserved for the per-warp mbarriers at the start of shared memory
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int GW, bool FMA>
+__global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant__ SmallParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int QPW = 32 / GW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;
+  double* ws = reinterpret_cast<double*>(smem_raw + P.bar_bytes) + (size_t)warp * P.tv.total;
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncwarp();
+
+  const long long total_warps = (long long)gridDim.x * warps_per_cta;
+  const long long my_warp = (long long)blockIdx.x * warps_per_cta + warp;
+  unsigned parity = 0;
+
+  auto next_tile = [&](long long prev) -> long long {
+    long long t;
+    if (P.ticket) {
+      unsigned v = 0;
+      if (lane == 0) v = atomicAdd(P.ticket, 1u);
+      t = (long long)__shfl_sync(MGQP_FULL, v, 0);
+    } else {
+      t = (prev < 0) ? my_warp : prev + total_warps;
+    }
+    return t;
+  };
+
+  long long tile = next_tile(-1);
+  while (tile < P.tiles) {
+    const long long q0 = tile * QPW;
+    const long long rem = P.batch - q0;
+    const int cnt = rem < QPW ? (int)rem : QPW;
+    const unsigned bulk = (cnt == QPW) ? P.bulk_mask : 0u;
+
+    // ---- stage the tile
+    if (bulk && lane == 0) {
+      mbar_expect_tx(bar, P.bulk_bytes);
+#pragma unroll
+      for (int k = 0; k < 6; k++)
+        if (bulk & (1u << k))
+          bulk_g2s(ws + P.off[k], P.in[k] + q0 * P.stride[k], (unsigned)(QPW * P.size[k] * 8), bar);
+    }
+    // fields that cannot go through TMA (odd alignment, broadcast or padded strides, tail tile):
+    // plain coalesced loads; groups beyond the tail replicate the tile's first QP
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if (!(bulk & (1u << k)) && P.size[k] > 0) {
+        const int sz = P.size[k], tot = QPW * sz;
+        for (int idx = lane; idx < tot; idx += 32) {
+          const int q = idx / sz, e = idx - q * sz;
+          const long long qq = q0 + (q < cnt ? q : 0);
+          ws[P.off[k] + idx] = __ldg(P.in[k] + qq * P.stride[k] + e);
+        }
+      }
+    }
+    // ---- next ticket now; pull that tile towards L2 while this one is being solved
+    const long long tile_next = next_tile(tile);
+    if (tile_next < P.tiles && lane < 6 && (P.bulk_mask & (1u << lane)) &&
+        (tile_next + 1) * QPW <= P.batch) {
+      bulk_prefetch_l2(P.in[lane] + tile_next * QPW * P.stride[lane], (unsigned)(QPW * P.size[lane] * 8));
+    }
+    if (bulk) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+    }
+    __syncwarp();
+
+    TileOut out;
+    out.x = P.x + q0 * P.tv.n;
+    out.f = P.f + q0;
+    out.status = P.status + q0;
+    out.iq = P.iq ? P.iq + q0 : nullptr;
+    out.A = P.A ? P.A + q0 * (P.tv.p + P.tv.m) : nullptr;
+    out.iters = P.iters ? P.iters + q0 : nullptr;
+    gi_solve_tile<GW, FMA>(P.tv, ws, cnt, P.max_iter, out);
+
+    // generic-proxy accesses to the block are done; order them before the next async-proxy write
+    fence_proxy_async();
+    __syncwarp();
+    tile = tile_next;
+  }
+}
+
+}  // namespace mgqp

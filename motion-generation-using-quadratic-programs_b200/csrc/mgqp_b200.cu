@@ -1,0 +1,449 @@
+// C-ABI of the B200 batched QP engine (declared in include/mgqp_b200.h).
+//
+// Replaces, for batches, the reference's only solver call
+//   sum = solve_quadprog(G, g0, t(CE), ce0, t(CI), ci0, x);          src/mgqp.cpp:708, :725
+// (prototype include/QuadProgpp/QuadProg++.hh:69-72, body in lib/QuadProgpp/libquadprog.a).
+// There is no CPU fallback in this file: without a CUDA device every entry point fails loudly.
+#include "../../include/mgqp_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "gi_small_kernel.cuh"
+
+namespace {
+
+using namespace mgqp;
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int rc, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return rc;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(MGQP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                       \
+  } while (0)
+
+constexpr int kMaxDev = 16;
+constexpr int kTicketRing = 256;
+
+struct DeviceCtx {
+  std::mutex mu;
+  bool init = false;
+  int sms = 0;
+  int smem_optin = 0;
+  unsigned* tickets = nullptr;  // ring of work-queue heads
+  unsigned ring_pos = 0;
+  bool attr_set[3][2] = {{false, false}, {false, false}, {false, false}};
+  int attr_smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+};
+DeviceCtx g_dev[kMaxDev];
+
+int device_ctx(int device, DeviceCtx** out) {
+  if (device < 0 || device >= kMaxDev) return fail(MGQP_ERR_INVALID_ARG, "device %d out of range", device);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(MGQP_ERR_NO_DEVICE, "no CUDA device available: this engine has no CPU fallback");
+  if (device >= count) return fail(MGQP_ERR_INVALID_ARG, "device %d >= device count %d", device, count);
+  DeviceCtx& c = g_dev[device];
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (!c.init) {
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU(cudaMalloc(&c.tickets, kTicketRing * sizeof(unsigned)));
+    CU(cudaMemset(c.tickets, 0, kTicketRing * sizeof(unsigned)));
+    c.init = true;
+  }
+  *out = &c;
+  return MGQP_OK;
+}
+
+struct Plan {
+  int gw = -1;         // lanes per QP (8/16/32); 0 = CTA-per-QP kernel; <0 unsupported
+  int warps = 0;       // warps per CTA
+  int smem = 0;        // dynamic shared memory per CTA
+  int bar_bytes = 0;
+  TileView tv;
+};
+
+// SM shared-memory budget used for planning when no device is queried (B200: 227 KB opt-in).
+constexpr int kSmemBudget = 227 * 1024;
+
+Plan make_plan(int n, int p, int m, int smem_optin) {
+  Plan pl;
+  if (n < 1 || p < 0 || m < 0) return pl;
+  int gw = n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 0;
+  while (gw && gw < 32 && m > 32 * gw) gw *= 2;
+  if (gw == 0 || m > 32 * gw) {
+    pl.gw = -2;
+    return pl;
+  }
+  for (;; gw *= 2) {
+    TileView tv = make_tile_view(n, p, m, gw);
+    const long long per_warp = (long long)tv.total * 8;
+    // one CTA per SM unless warps are small; leave the 1 KB/CTA the driver reserves
+    int warps = (int)((smem_optin - 1024 - 256) / per_warp);
+    if (warps >= 1) {
+      if (warps > 16) warps = 16;
+      pl.gw = gw;
+      pl.warps = warps;
+      pl.tv = tv;
+      pl.bar_bytes = ((warps * 8) + 15) & ~15;
+      pl.smem = pl.bar_bytes + (int)(per_warp * warps);
+      return pl;
+    }
+    if (gw == 32) break;
+  }
+  pl.gw = -2;
+  return pl;
+}
+
+template <int GW, bool FMA>
+int launch_small(DeviceCtx* ctx, const Plan& pl, const SmallParams& P, cudaStream_t st, int gi, int fi) {
+  auto kern = gi_small_kernel<GW, FMA>;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->attr_set[gi][fi] || ctx->attr_smem[gi][fi] < pl.smem) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+      ctx->attr_set[gi][fi] = true;
+      ctx->attr_smem[gi][fi] = pl.smem;
+    }
+  }
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl.warps * 32, pl.smem));
+  if (per_sm < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "kernel does not fit an SM (smem %d B)", pl.smem);
+  long long ctas = (long long)ctx->sms * per_sm;
+  const long long need = (P.tiles + pl.warps - 1) / pl.warps;
+  if (ctas > need) ctas = need;
+  if (ctas < 1) ctas = 1;
+  kern<<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(P);
+  g_launches.fetch_add(1);
+  CU(cudaGetLastError());
+  return MGQP_OK;
+}
+
+int validate(const mgqp_batch* d) {
+  if (!d) return fail(MGQP_ERR_INVALID_ARG, "null batch descriptor");
+  if (d->n < 1) return fail(MGQP_ERR_INVALID_ARG, "n = %d must be >= 1", d->n);
+  if (d->p < 0 || d->m < 0) return fail(MGQP_ERR_INVALID_ARG, "p = %d, m = %d must be >= 0", d->p, d->m);
+  if (d->batch < 0) return fail(MGQP_ERR_INVALID_ARG, "batch = %lld must be >= 0", (long long)d->batch);
+  if (!d->G || !d->g0 || (d->p && (!d->CE || !d->ce0)) || (d->m && (!d->CI || !d->ci0)))
+    return fail(MGQP_ERR_INVALID_ARG, "null input pointer");
+  if (!d->x || !d->f || !d->status) return fail(MGQP_ERR_INVALID_ARG, "null output pointer (x, f, status are required)");
+  if (d->sG < 0 || d->sg0 < 0 || d->sCE < 0 || d->sce0 < 0 || d->sCI < 0 || d->sci0 < 0)
+    return fail(MGQP_ERR_INVALID_ARG, "negative stride");
+  return MGQP_OK;
+}
+
+int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (d->batch == 0) return MGQP_OK;
+  DeviceCtx* ctx = nullptr;
+  if ((rc = device_ctx(device, &ctx))) return rc;
+  CU(cudaSetDevice(device));
+  const Plan pl = make_plan(d->n, d->p, d->m, ctx->smem_optin);
+  if (pl.gw < 0)
+    return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "shape n=%d p=%d m=%d is outside the kernels built so far (n <= 32)", d->n,
+                d->p, d->m);
+
+  SmallParams P;
+  memset(&P, 0, sizeof P);
+  P.tv = pl.tv;
+  P.batch = d->batch;
+  const int qpw = pl.tv.qpw;
+  P.tiles = (d->batch + qpw - 1) / qpw;
+  const double* in[6] = {d->G, d->g0, d->CE, d->ce0, d->CI, d->ci0};
+  const long long stride[6] = {d->sG, d->sg0, d->sCE, d->sce0, d->sCI, d->sci0};
+  const int size[6] = {d->n * d->n, d->n, d->n * d->p, d->p, d->n * d->m, d->m};
+  const int off[6] = {pl.tv.oG, pl.tv.og0, pl.tv.oCE, pl.tv.oce0, pl.tv.oCI, pl.tv.oci0};
+  P.bulk_mask = 0;
+  P.bulk_bytes = 0;
+  for (int k = 0; k < 6; k++) {
+    P.in[k] = in[k];
+    P.stride[k] = stride[k];
+    P.size[k] = size[k];
+    P.off[k] = off[k];
+    const long long bytes = (long long)qpw * size[k] * 8;
+    const bool ok = !(d->flags & MGQP_FLAG_NO_BULK_COPY) && size[k] > 0 && stride[k] == size[k] &&
+                    (bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(in[k]) % 16) == 0;
+    if (ok) {
+      P.bulk_mask |= 1u << k;
+      P.bulk_bytes += (unsigned)bytes;
+    }
+  }
+  P.x = d->x;
+  P.f = d->f;
+  P.status = d->status;
+  P.iq = d->iq;
+  P.A = d->A;
+  P.iters = d->iters;
+  P.max_iter = d->max_iter > 0 ? d->max_iter : 100 + 10 * (d->p + d->m);
+  P.bar_bytes = pl.bar_bytes;
+  P.ticket = nullptr;
+  if (!(d->flags & MGQP_FLAG_STATIC_SCHEDULE)) {
+    unsigned slot;
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      slot = ctx->ring_pos++ % kTicketRing;
+    }
+    P.ticket = ctx->tickets + slot;
+    CU(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned), st));
+  }
+  const bool fast = (d->flags & MGQP_FLAG_FAST_MATH) != 0;
+  const int gi = pl.gw == 8 ? 0 : pl.gw == 16 ? 1 : 2;
+  if (pl.gw == 8) return fast ? launch_small<8, true>(ctx, pl, P, st, gi, 1) : launch_small<8, false>(ctx, pl, P, st, gi, 0);
+  if (pl.gw == 16) return fast ? launch_small<16, true>(ctx, pl, P, st, gi, 1) : launch_small<16, false>(ctx, pl, P, st, gi, 0);
+  return fast ? launch_small<32, true>(ctx, pl, P, st, gi, 1) : launch_small<32, false>(ctx, pl, P, st, gi, 0);
+}
+
+// ------------------------------------------------------------------ host-buffer pipeline
+struct DevBufs {
+  double *G = nullptr, *g0 = nullptr, *CE = nullptr, *ce0 = nullptr, *CI = nullptr, *ci0 = nullptr, *x = nullptr, *f = nullptr;
+  int *status = nullptr, *iq = nullptr, *A = nullptr, *iters = nullptr;
+  void* all[12] = {};
+  int free_all() {
+    for (void* p : all)
+      if (p) cudaFree(p);
+    return 0;
+  }
+};
+
+int alloc_bufs(DevBufs& b, const mgqp_batch* h, long long chunk) {
+  const long long n = h->n, p = h->p, m = h->m;
+  auto al = [&](void** dst, long long bytes, int slot) -> int {
+    if (bytes <= 0) bytes = 16;
+    CU(cudaMalloc(dst, (size_t)bytes));
+    b.all[slot] = *dst;
+    return MGQP_OK;
+  };
+  int rc;
+  if ((rc = al((void**)&b.G, chunk * n * n * 8, 0))) return rc;
+  if ((rc = al((void**)&b.g0, chunk * n * 8, 1))) return rc;
+  if ((rc = al((void**)&b.CE, chunk * n * p * 8, 2))) return rc;
+  if ((rc = al((void**)&b.ce0, chunk * p * 8, 3))) return rc;
+  if ((rc = al((void**)&b.CI, chunk * n * m * 8, 4))) return rc;
+  if ((rc = al((void**)&b.ci0, chunk * m * 8, 5))) return rc;
+  if ((rc = al((void**)&b.x, chunk * n * 8, 6))) return rc;
+  if ((rc = al((void**)&b.f, chunk * 8, 7))) return rc;
+  if ((rc = al((void**)&b.status, chunk * 4, 8))) return rc;
+  if (h->iq && (rc = al((void**)&b.iq, chunk * 4, 9))) return rc;
+  if (h->A && (rc = al((void**)&b.A, chunk * (p + m) * 4, 10))) return rc;
+  if (h->iters && (rc = al((void**)&b.iters, chunk * 4, 11))) return rc;
+  return MGQP_OK;
+}
+
+// Upload / solve / download QPs [q0, q0+cnt) of host batch h through buffers b on stream st.
+int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long long cnt, cudaStream_t st) {
+  const long long n = h->n, p = h->p, m = h->m;
+  mgqp_batch d = *h;
+  d.batch = cnt;
+  struct F { const double* src; long long stride, size; double* dst; const double** dptr; int64_t* dstride; };
+  F fs[6] = {{h->G, h->sG, n * n, b.G, &d.G, &d.sG},       {h->g0, h->sg0, n, b.g0, &d.g0, &d.sg0},
+             {h->CE, h->sCE, n * p, b.CE, &d.CE, &d.sCE},  {h->ce0, h->sce0, p, b.ce0, &d.ce0, &d.sce0},
+             {h->CI, h->sCI, n * m, b.CI, &d.CI, &d.sCI},  {h->ci0, h->sci0, m, b.ci0, &d.ci0, &d.sci0}};
+  for (auto& f : fs) {
+    *f.dptr = f.dst;
+    if (f.size == 0) { *f.dstride = 0; continue; }
+    if (f.stride == 0) {  // broadcast field: one instance
+      CU(cudaMemcpyAsync(f.dst, f.src, (size_t)f.size * 8, cudaMemcpyHostToDevice, st));
+      *f.dstride = 0;
+    } else if (f.stride == f.size) {
+      CU(cudaMemcpyAsync(f.dst, f.src + q0 * f.stride, (size_t)(cnt * f.size) * 8, cudaMemcpyHostToDevice, st));
+      *f.dstride = f.size;
+    } else {  // padded host layout: compact it on the way up
+      CU(cudaMemcpy2DAsync(f.dst, (size_t)f.size * 8, f.src + q0 * f.stride, (size_t)f.stride * 8, (size_t)f.size * 8,
+                           (size_t)cnt, cudaMemcpyHostToDevice, st));
+      *f.dstride = f.size;
+    }
+  }
+  d.x = b.x; d.f = b.f; d.status = b.status;
+  d.iq = h->iq ? b.iq : nullptr;
+  d.A = h->A ? b.A : nullptr;
+  d.iters = h->iters ? b.iters : nullptr;
+  int rc = solve_device(&d, device, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->x + q0 * n, b.x, (size_t)(cnt * n) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->f + q0, b.f, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->status + q0, b.status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+  if (h->iq) CU(cudaMemcpyAsync(h->iq + q0, b.iq, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+  if (h->A) CU(cudaMemcpyAsync(h->A + q0 * (p + m), b.A, (size_t)(cnt * (p + m)) * 4, cudaMemcpyDeviceToHost, st));
+  if (h->iters) CU(cudaMemcpyAsync(h->iters + q0, b.iters, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+  return MGQP_OK;
+}
+
+long long default_chunk(const mgqp_batch* h) {
+  const long long per_qp = mgqp_algorithmic_bytes(h->n, h->p, h->m);
+  long long c = (256ll << 20) / (per_qp > 0 ? per_qp : 1);  // ~256 MB of inputs per chunk
+  if (c < 1024) c = 1024;
+  c &= ~1023ll;
+  return c;
+}
+
+// Pull chunks from `next` until the batch is exhausted; two streams, two buffer sets.
+int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long>* next) {
+  int rc = validate(h);
+  if (rc) return rc;
+  DeviceCtx* ctx = nullptr;
+  if ((rc = device_ctx(device, &ctx))) return rc;
+  CU(cudaSetDevice(device));
+  if (chunk > h->batch) chunk = h->batch;
+  if (chunk < 1) return MGQP_OK;
+  cudaStream_t st[2];
+  DevBufs bufs[2];
+  for (int i = 0; i < 2; i++) {
+    CU(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    if ((rc = alloc_bufs(bufs[i], h, chunk))) break;
+  }
+  int k = 0;
+  while (!rc) {
+    const long long q0 = next->fetch_add(chunk);
+    if (q0 >= h->batch) break;
+    const long long cnt = (h->batch - q0) < chunk ? (h->batch - q0) : chunk;
+    // the buffer set is reused every second chunk: wait for its previous occupant
+    if (cudaStreamSynchronize(st[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "stream sync failed"); break; }
+    rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1]);
+    k++;
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaError_t e = cudaStreamSynchronize(st[i]);
+    if (e != cudaSuccess && !rc) rc = fail(MGQP_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    cudaStreamDestroy(st[i]);
+    bufs[i].free_all();
+  }
+  return rc;
+}
+
+}  // namespace
+
+// ====================================================================== exported C ABI
+extern "C" {
+
+int solve_quadprog_batched(const mgqp_batch* d, int device, void* stream) {
+  return solve_device(d, device, static_cast<cudaStream_t>(stream));
+}
+
+int solve_quadprog_batched_host(const mgqp_batch* h, int device, int64_t chunk) {
+  int rc = validate(h);
+  if (rc) return rc;
+  if (chunk <= 0) chunk = default_chunk(h);
+  std::atomic<long long> next(0);
+  return pump(h, device, chunk, &next);
+}
+
+int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int ndev, int64_t chunk) {
+  int rc = validate(h);
+  if (rc) return rc;
+  if (!devices || ndev < 1) return fail(MGQP_ERR_INVALID_ARG, "need at least one device");
+  if (chunk <= 0) {
+    chunk = default_chunk(h);
+    // at least ~4 chunks per device so the dynamic sharding can balance
+    while (chunk > 1024 && h->batch / chunk < 4ll * ndev) chunk /= 2;
+  }
+  std::atomic<long long> next(0);
+  std::vector<int> rcs(ndev, 0);
+  std::vector<std::string> errs(ndev);
+  std::vector<std::thread> th;
+  for (int i = 0; i < ndev; i++)
+    th.emplace_back([&, i]() {
+      rcs[i] = pump(h, devices[i], chunk, &next);
+      if (rcs[i]) errs[i] = g_last_error;
+    });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < ndev; i++)
+    if (rcs[i]) return fail(rcs[i], "device %d: %s", devices[i], errs[i].c_str());
+  return MGQP_OK;
+}
+
+int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const double* g0, const double* CE,
+                   const double* ce0, const double* CI, const double* ci0, double* x, double* f, int32_t* status,
+                   double* G_factor, int device) {
+  mgqp_batch h;
+  memset(&h, 0, sizeof h);
+  h.n = n; h.p = p; h.m = m; h.batch = 1;
+  h.G = G; h.g0 = g0; h.CE = CE; h.ce0 = ce0; h.CI = CI; h.ci0 = ci0;
+  h.sG = (int64_t)n * n; h.sg0 = n; h.sCE = (int64_t)n * p; h.sce0 = p; h.sCI = (int64_t)n * m; h.sci0 = m;
+  h.x = x; h.f = f; h.status = status;
+  // empty blocks may come in as null pointers (Matrix(n,0)); give validate() something to look at
+  static const double dummy = 0.0;
+  if (p == 0) { h.CE = &dummy; h.ce0 = &dummy; }
+  if (m == 0) { h.CI = &dummy; h.ci0 = &dummy; }
+  int rc = solve_quadprog_batched_host(&h, device, 1);
+  if (rc) return rc;
+  if (G_factor) {
+    // The reference leaves chol(G) in G (lower factor mirrored into the upper triangle,
+    // QuadProg++.hh:42-45).  n is tiny on this path; the factor is recomputed on the host in the
+    // reference's operation order so the caller sees the same bits.
+    for (int i = 0; i < n * n; i++) G_factor[i] = G[i];
+    for (int i = 0; i < n; i++) {
+      for (int j = i; j < n; j++) {
+        double sum = G_factor[i * n + j];
+        for (int k = i - 1; k >= 0; k--) sum -= G_factor[i * n + k] * G_factor[j * n + k];
+        if (i == j) {
+          if (sum <= 0.0) return MGQP_OK;  // status already says NOT_PD
+          G_factor[i * n + i] = sqrt(sum);
+        } else {
+          G_factor[j * n + i] = sum / G_factor[i * n + i];
+        }
+      }
+      for (int k = i + 1; k < n; k++) G_factor[i * n + k] = G_factor[k * n + i];
+    }
+  }
+  return MGQP_OK;
+}
+
+const char* mgqp_status_string(int status) {
+  switch (status) {
+    case MGQP_STATUS_OK: return "ok";
+    case MGQP_STATUS_INFEASIBLE: return "infeasible";
+    case MGQP_STATUS_NOT_PD: return "G not positive definite";
+    case MGQP_STATUS_EQ_DEPENDENT: return "Constraints are linearly dependent";
+    case MGQP_STATUS_ITER_CAP: return "iteration cap reached";
+    default: return "unknown";
+  }
+}
+
+const char* mgqp_last_error(void) { return g_last_error.c_str(); }
+
+int mgqp_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+
+int64_t mgqp_kernel_launch_count(void) { return g_launches.load(); }
+
+int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int32_t* warps_per_cta) {
+  const Plan pl = make_plan(n, p, m, kSmemBudget);
+  if (smem_bytes_per_cta) *smem_bytes_per_cta = pl.smem;
+  if (warps_per_cta) *warps_per_cta = pl.warps;
+  return pl.gw;
+}
+
+int64_t mgqp_algorithmic_bytes(int32_t n, int32_t p, int32_t m) {
+  const int64_t N = n, P = p, M = m;
+  return 8 * (N * N + N + N * P + P + N * M + M) + 8 * (N + 1) + 4;
+}
+
+}  // extern "C"

@@ -29,6 +29,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* test instrumentation: how often the degenerate-add branch ran (not thread-safe; tests use 1 thread) */
+long long gi_oracle_degenerate_count = 0;
+
 #define GI_EPS 2.220446049250313e-16 /* std::numeric_limits<double>::epsilon(), .rodata+0x190 */
 
 /* QuadProg++ `distance` (weak symbol in QuadProg++.o): overflow-safe sqrt(a^2+b^2). */
@@ -53,13 +56,16 @@ static double gi_dot(const double* a, const double* b, int n) {
 
 /* cholesky_decomposition (QuadProg++.o+0x2df0; same arithmetic as ArrayHelpers.hh:66-99).
  * Returns 0, or 1 when a pivot is <= 0 (the reference prints the matrix and throws). */
-static int gi_cholesky(double* G, int n) {
+static int gi_cholesky(double* G, int n, double* bad_pivot) {
   for (int i = 0; i < n; i++) {
     for (int j = i; j < n; j++) {
       double sum = G[i * n + j];
       for (int k = i - 1; k >= 0; k--) sum -= G[i * n + k] * G[j * n + k];
       if (i == j) {
-        if (sum <= 0.0) return 1;
+        if (sum <= 0.0) {
+          *bad_pivot = sum; /* the value the reference prints in its exception text */
+          return 1;
+        }
         G[i * n + i] = sqrt(sum);
       } else {
         G[j * n + i] = sum / G[i * n + i];
@@ -214,9 +220,8 @@ int gi_oracle_solve(int n, int p, int m, double* G, const double* g0, const doub
 
   c1 = 0.0;
   for (int i = 0; i < n; i++) c1 += G[i * n + i];
-  if (gi_cholesky(G, n)) {
-    status = GI_NOT_PD;
-    f_value = NAN;
+  if (gi_cholesky(G, n, &f_value)) {
+    status = GI_NOT_PD; /* f reports the non-positive pivot ("Error in cholesky decomposition, sum: ...") */
     goto done;
   }
   R_norm = 1.0;
@@ -330,6 +335,7 @@ l2a:
   u[iq] += t;
   if (fabs(t - t2) < GI_EPS) {
     if (!gi_add_constraint(R, J, d, &iq, &R_norm, n)) {
+      gi_oracle_degenerate_count++;
       iaexcl[ip] = 0;
       gi_delete_constraint(R, J, A, u, n, p, &iq, ip);
       for (int i = 0; i < m; i++) iai[i] = i;

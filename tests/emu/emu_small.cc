@@ -1,0 +1,75 @@
+// TEST INFRASTRUCTURE: runs the DEVICE solver body (csrc/gi_small.cuh) on the CPU under the fiber
+// warp emulator, so that its lock-step logic can be compared bit-for-bit with the oracle here,
+// where there is no GPU.  Build: g++ -O1 -ffp-contract=off -DMGQP_EMULATE -shared -fPIC ...
+#include "warp_emu.h"
+#include "../../motion-generation-using-quadratic-programs_b200/csrc/gi_small.cuh"
+
+#include <thread>
+#include <vector>
+#include <atomic>
+
+using namespace mgqp;
+
+namespace {
+struct Job {
+  TileView tv;
+  double* ws;
+  int cnt, max_iter, gw, fma;
+  TileOut out;
+};
+
+void lane_body(void* a) {
+  Job* j = (Job*)a;
+  if (j->fma) {
+    if (j->gw == 8) gi_solve_tile<8, true>(j->tv, j->ws, j->cnt, j->max_iter, j->out);
+    else if (j->gw == 16) gi_solve_tile<16, true>(j->tv, j->ws, j->cnt, j->max_iter, j->out);
+    else gi_solve_tile<32, true>(j->tv, j->ws, j->cnt, j->max_iter, j->out);
+  } else {
+    if (j->gw == 8) gi_solve_tile<8, false>(j->tv, j->ws, j->cnt, j->max_iter, j->out);
+    else if (j->gw == 16) gi_solve_tile<16, false>(j->tv, j->ws, j->cnt, j->max_iter, j->out);
+    else gi_solve_tile<32, false>(j->tv, j->ws, j->cnt, j->max_iter, j->out);
+  }
+}
+}  // namespace
+
+extern "C" int emu_solve_batch(int n, int p, int m, long long batch, const double* G, const double* g0,
+                               const double* CE, const double* ce0, const double* CI, const double* ci0,
+                               double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
+                               int gw, int fma, int threads) {
+  if (n > gw || m > 32 * gw) return -2;
+  const TileView tv = make_tile_view(n, p, m, gw);
+  const int qpw = tv.qpw;
+  const long long tiles = (batch + qpw - 1) / qpw;
+  if (max_iter <= 0) max_iter = 100 + 10 * (p + m);
+  std::atomic<long long> next(0);
+  auto work = [&]() {
+    std::vector<double> ws(tv.total);
+    for (;;) {
+      const long long t = next.fetch_add(1);
+      if (t >= tiles) break;
+      const long long q0 = t * qpw;
+      const int cnt = (int)((batch - q0) < qpw ? (batch - q0) : qpw);
+      for (int g = 0; g < qpw; g++) {
+        const long long q = q0 + (g < cnt ? g : 0);  // tail groups replicate the tile's first QP
+        memcpy(&ws[tv.oG + g * n * n], G + q * n * n, sizeof(double) * n * n);
+        memcpy(&ws[tv.og0 + g * n], g0 + q * n, sizeof(double) * n);
+        memcpy(&ws[tv.oCE + g * n * p], CE + q * n * p, sizeof(double) * n * p);
+        memcpy(&ws[tv.oce0 + g * p], ce0 + q * p, sizeof(double) * p);
+        memcpy(&ws[tv.oCI + g * n * m], CI + q * n * m, sizeof(double) * n * m);
+        memcpy(&ws[tv.oci0 + g * m], ci0 + q * m, sizeof(double) * m);
+      }
+      Job j;
+      j.tv = tv; j.ws = ws.data(); j.cnt = cnt; j.max_iter = max_iter; j.gw = gw; j.fma = fma;
+      j.out.x = x + q0 * n; j.out.f = f + q0; j.out.status = status + q0;
+      j.out.iq = iq ? iq + q0 : nullptr;
+      j.out.A = A ? A + q0 * (p + m) : nullptr;
+      j.out.iters = iters ? iters + q0 : nullptr;
+      emu_run_warp(lane_body, &j);
+    }
+  };
+  if (threads <= 1) { work(); return 0; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  return 0;
+}

@@ -1,0 +1,81 @@
+"""CPU: the DEVICE solver body (csrc/gi_small.cuh) compiled for the host and run under a fiber warp
+emulator (tests/emu) must be bit-identical to the oracle -- x, f, verdict, active set, step count.
+This checks the lock-step control flow (predicated dual/full/partial/degenerate branches, warp
+primitives in uniform control flow) without a GPU; the GPU tests then only have to establish that
+the hardware executes the same program."""
+import numpy as np
+import pytest
+
+from conftest import default_max_iter
+from helpers import assert_bit_identical, assert_parity, emu_solve
+from mgqp_b200 import workloads
+
+
+def _oracle(restatement, b, max_iter=0):
+    return restatement.solve_batch(b.n, b.p, b.m, *b.fields(), max_iter=max_iter or default_max_iter(b.p, b.m), threads=4)
+
+
+@pytest.mark.parametrize("name,B,gw", [("C2", 403, 8), ("C5", 402, 8), ("C3", 203, 16), ("S0", 201, 16),
+                                       ("S2", 201, 16), ("C2", 61, 16), ("C2", 33, 32)])
+def test_benchmark_shapes(emu_lib, restatement, name, B, gw):
+    b = workloads.make(name, B)
+    assert_bit_identical(emu_solve(emu_lib, b, gw), _oracle(restatement, b), f"{name}/gw{gw}")
+
+
+@pytest.mark.parametrize("n,p,m,gw", [(5, 2, 12, 8), (8, 0, 20, 8), (8, 3, 9, 8), (3, 1, 0, 8), (7, 0, 0, 8),
+                                      (12, 4, 30, 16), (16, 2, 40, 16), (20, 5, 50, 32), (32, 4, 70, 32),
+                                      (1, 0, 3, 8), (2, 1, 3, 8), (8, 8, 4, 8), (6, 0, 200, 8)])
+def test_random_shapes(emu_lib, restatement, n, p, m, gw):
+    b = workloads.make_random(67, n, p, m, seed=n * 100 + m)
+    assert_bit_identical(emu_solve(emu_lib, b, gw), _oracle(restatement, b), f"R{n}_{p}_{m}")
+
+
+def test_failure_verdicts(emu_lib, restatement):
+    """Not-PD G, dependent equalities and infeasible bounds mixed into one batch (each group of
+    lanes must retire on its own verdict while its warp-mates keep iterating)."""
+    b = workloads.make_random(64, 6, 2, 14, seed=11, box=True)
+    for i in range(0, 64, 4):
+        b.CE[i, :, 1] = -0.5 * b.CE[i, :, 0]      # status 3
+    for i in range(1, 64, 8):
+        b.G[i] -= 4.0 * np.eye(6)                  # status 2
+    for i in range(2, 64, 8):
+        b.ci0[i, 0] = -3.0; b.ci0[i, 6] = 1.0      # x0 >= 3 and x0 <= 1: status 1
+    ref = _oracle(restatement, b)
+    assert set(np.unique(ref["status"])) >= {0, 1, 2, 3}
+    got = emu_solve(emu_lib, b, 8)
+    assert np.array_equal(got["status"], ref["status"])
+    keep = ref["status"] != 2   # after a failed Cholesky the reference has thrown: x, iq are not defined
+    for k in ("x", "iq", "iters", "A"):
+        assert np.array_equal(got[k][keep], ref[k][keep]), k
+    assert np.array_equal(got["f"], ref["f"], equal_nan=True)  # status 2: f carries the bad pivot
+
+
+def _degenerate_batch(B=96):
+    """Badly scaled constraint normals: once a 1e10-scaled bound is active, R_norm ~ 1e10 and adding a
+    1e-7-scaled one fails add_constraint's |d[iq]| <= eps*R_norm test while z.z > eps still holds, i.e.
+    the reference's degenerate branch (note N3: it then usually spins forever)."""
+    b = workloads.make_random(B, 5, 1, 12, seed=3)
+    b.CI[:, :, 0:6] *= 1e10; b.ci0[:, 0:6] *= 1e10
+    b.CI[:, :, 6:12] *= 1e-7; b.ci0[:, 6:12] *= 1e-7
+    b.g0 *= 4.0
+    return b
+
+
+def test_degenerate_branch_and_iteration_cap(emu_lib, restatement):
+    import ctypes as C
+    b = _degenerate_batch()
+    cnt = C.c_longlong.in_dll(restatement.lib, "gi_oracle_degenerate_count")
+    for cap in (7, 60):
+        cnt.value = 0
+        ref = restatement.solve_batch(b.n, b.p, b.m, *b.fields(), max_iter=cap, threads=1)
+        assert cnt.value > 50, "the batch is meant to exercise the degenerate-add branch"
+        got = emu_solve(emu_lib, b, 8, max_iter=cap)
+        assert_bit_identical(got, ref, f"cap{cap}")
+    assert (ref["status"] == 4).any() and (ref["status"] == 0).any()
+
+
+def test_fast_math_mode_within_tolerance(emu_lib, restatement):
+    """FMA + tree reductions: not bit-identical by design, but inside the 1e-9 gate."""
+    b = workloads.make("C2", 301)
+    got = emu_solve(emu_lib, b, 8, fma=1)
+    assert_parity(got, _oracle(restatement, b), "C2/fast")
