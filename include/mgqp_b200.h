@@ -62,7 +62,10 @@ enum {
   /* Stage inputs with plain coalesced loads instead of TMA bulk copies (debug / odd alignments). */
   MGQP_FLAG_NO_BULK_COPY = 2,
   /* Static round-robin tile assignment instead of the persistent atomic work queue. */
-  MGQP_FLAG_STATIC_SCHEDULE = 4
+  MGQP_FLAG_STATIC_SCHEDULE = 4,
+  /* Always use the lane-group kernel (8/16/32 lanes per QP), even where the one-QP-per-lane
+   * kernel (n <= 8, m <= 64) would be picked. */
+  MGQP_FLAG_GROUP_KERNEL = 8
 };
 
 /* One batch of `batch` independent QPs of one shape, field-wise SoA, DEVICE pointers.
@@ -115,7 +118,7 @@ const char* mgqp_last_error(void);        /* thread-local text of the last non-O
 int mgqp_device_count(void);
 /* Kernel launches issued by this library in this process (all threads); for bench bookkeeping. */
 int64_t mgqp_kernel_launch_count(void);
-/* Which kernel family a shape maps to: 8/16/32 = lanes per QP of the warp kernel, 0 = CTA-per-QP
+/* Which kernel family a shape maps to: 1 = one QP per lane, 8/16/32 = lanes per QP of the warp kernel, 0 = CTA-per-QP
  * kernel, <0 = unsupported.  smem_bytes_per_cta / ctas_per_sm (optional) receive the launch plan. */
 int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int32_t* warps_per_cta);
 /* Compulsory HBM bytes per QP for a shape (every input once, x/f/status once); SURVEY.md 8(d). */

@@ -1,0 +1,137 @@
+// Persistent kernel around gi_lane_solve: every WARP is an independent worker that pulls tiles of
+// 32 consecutive QPs from the atomic work queue; lane q of the warp owns QP q of the tile.
+//
+// Staging (the one HBM read of every input byte) is cooperative and coalesced: the 32 lanes sweep
+// the tile's contiguous [32][n*m] block of CI one QP after the other, parking each chunk in the
+// owner lane's (still unused) J|R area, and every lane then classifies the columns of its own QP
+// from shared memory (gi_lane.cuh).  G, g0 and ci0 take the same route.  The next tile is
+// prefetched into L2 with cp.async.bulk.prefetch while the current one is solved.
+#pragma once
+#include "gi_lane.cuh"
+
+namespace mgqp {
+
+struct LaneParams {
+  LaneView v;
+  long long batch, tiles;
+  const double* in[6];   // G, g0, CE, ce0, CI, ci0
+  long long stride[6];
+  double* x; double* f; int* status; int* iq; int* A; int* iters;
+  int max_iter;
+  unsigned* ticket;
+  unsigned prefetch_mask;  // fields whose next-tile block is contiguous and 16-byte aligned
+};
+
+__device__ __forceinline__ void lane_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+template <int N, bool FMA>
+__global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__ LaneParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const LaneView& v = P.v;
+  const int n = N, p = v.p, m = v.m, stride = v.stride;
+  double* ws = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 32 * stride;
+  double* S = ws + lane * stride;
+  const long long total_warps = (long long)gridDim.x * warps_per_cta;
+  const long long my_warp = (long long)blockIdx.x * warps_per_cta + warp;
+  const int sizes[6] = {n * n, n, n * p, p, n * m, m};
+
+  auto next_tile = [&](long long prev) -> long long {
+    if (P.ticket) {
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(P.ticket, 1u);
+      return (long long)__shfl_sync(MGQP_FULL, t, 0);
+    }
+    return (prev < 0) ? my_warp : prev + total_warps;
+  };
+
+  long long tile = next_tile(-1);
+  while (tile < P.tiles) {
+    const long long q0 = tile * 32;
+    const long long rem = P.batch - q0;
+    const int cnt = rem < 32 ? (int)rem : 32;
+    const long long tile_next = next_tile(tile);
+    if (tile_next < P.tiles && (tile_next + 1) * 32 <= P.batch && lane < 6 && (P.prefetch_mask & (1u << lane))) {
+      // one contiguous block per field: 32 QPs x size doubles (<= 75 KB for CI at n=7, m=42)
+      const char* src = reinterpret_cast<const char*>(P.in[lane] + tile_next * 32 * P.stride[lane]);
+      unsigned bytes = 32u * (unsigned)sizes[lane] * 8u;
+      while (bytes) {  // the prefetch size field is limited; go in 16 KB pieces
+        const unsigned b = bytes > 16384u ? 16384u : bytes;
+        lane_prefetch_l2(src, b);
+        src += b;
+        bytes -= b;
+      }
+    }
+
+    // ---- CI: stream through the J|R area in chunks, classify columns
+    int* I = reinterpret_cast<int*>(S + v.oInt);
+    for (int i = 0; i < m; i++) I[v.icidx + i] = LN_EMPTY;
+    const int nm = n * m;
+    const int CH = 2 * n * n;  // J|R are contiguous and free at this point
+    for (int e0 = 0; e0 < nm; e0 += CH) {
+      const int c = (nm - e0) < CH ? (nm - e0) : CH;
+      __syncwarp();
+      for (int q = 0; q < 32; q++) {
+        const long long qq = q0 + (q < cnt ? q : 0);
+        const double* src = P.in[4] + qq * P.stride[4] + e0;
+        double* dst = ws + q * stride + v.oJ;
+        for (int off = lane; off < c; off += 32) dst[off] = __ldg(src + off);
+      }
+      __syncwarp();
+      ln_classify(S, v, v.oJ, e0, c);
+    }
+    __syncwarp();
+    // ---- G -> R area, g0 -> d, ci0
+    for (int q = 0; q < 32; q++) {
+      const long long qq = q0 + (q < cnt ? q : 0);
+      double* Sq = ws + q * stride;
+      const double* g = P.in[0] + qq * P.stride[0];
+      for (int off = lane; off < n * n; off += 32) Sq[v.oR + off] = __ldg(g + off);
+      if (lane < n) Sq[v.od + lane] = __ldg(P.in[1] + qq * P.stride[1] + lane);
+      const double* c0 = P.in[5] + qq * P.stride[5];
+      for (int off = lane; off < m; off += 32) Sq[v.oci0 + off] = __ldg(c0 + off);
+    }
+    __syncwarp();
+
+    const long long myq = q0 + (lane < cnt ? lane : 0);
+    LaneIO io;
+    io.G = P.in[0] + myq * P.stride[0];
+    io.g0 = P.in[1] + myq * P.stride[1];
+    io.CE = P.in[2] + myq * P.stride[2];
+    io.ce0 = P.in[3] + myq * P.stride[3];
+    io.CI = P.in[4] + myq * P.stride[4];
+    io.ci0 = P.in[5] + myq * P.stride[5];
+    double xo[N];
+    double f;
+    int status, iq, iters;
+    gi_lane_solve<N, FMA>(v, S, io, P.max_iter, xo, f, status, iq, iters);
+    __syncwarp();
+
+    // ---- results: x through shared memory so that the global stores are coalesced
+#pragma unroll
+    for (int k = 0; k < N; k++) S[v.ox + k] = xo[k];
+    __syncwarp();
+    for (int e = lane; e < cnt * n; e += 32) {
+      const int q = e / n, k = e - q * n;
+      P.x[q0 * n + e] = ws[q * stride + v.ox + k];
+    }
+    if (lane < cnt) {
+      P.f[q0 + lane] = f;
+      P.status[q0 + lane] = status;
+      if (P.iq) P.iq[q0 + lane] = iq;
+      if (P.iters) P.iters[q0 + lane] = iters;
+      if (P.A) {
+        int* Ag = P.A + (q0 + lane) * (long long)(p + m);
+        const int* Aq = I + v.iA;
+        for (int i = 0; i < p + m; i++) Ag[i] = (i < iq) ? Aq[i] : 0x7fffffff;
+      }
+    }
+    __syncwarp();
+    tile = tile_next;
+  }
+}
+
+}  // namespace mgqp

@@ -18,6 +18,7 @@
 #include <thread>
 #include <vector>
 
+#include "gi_lane_kernel.cuh"
 #include "gi_small_kernel.cuh"
 
 namespace {
@@ -56,6 +57,7 @@ struct DeviceCtx {
   unsigned ring_pos = 0;
   bool attr_set[3][2] = {{false, false}, {false, false}, {false, false}};
   int attr_smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  int lane_attr_smem[9][2] = {};
 };
 DeviceCtx g_dev[kMaxDev];
 
@@ -143,6 +145,65 @@ int launch_small(DeviceCtx* ctx, const Plan& pl, const SmallParams& P, cudaStrea
   return MGQP_OK;
 }
 
+
+// ---------------------------------------------------------------- lane-per-QP family (n <= 8)
+struct LanePlan {
+  bool ok = false;
+  int warps = 0, smem = 0;
+  LaneView v;
+};
+
+LanePlan make_lane_plan(int n, int p, int m, int smem_optin) {
+  LanePlan lp;
+  if (n < 1 || n > 8 || m > 64 || p > n) return lp;
+  lp.v = make_lane_view(n, p, m);
+  const long long per_warp = 32ll * lp.v.stride * 8;
+  int warps = (int)((smem_optin - 1024) / per_warp);
+  if (warps < 2) return lp;  // one warp per SM cannot hide anything: use the lane-group kernel instead
+  if (warps > 8) warps = 8;
+  lp.warps = warps;
+  lp.smem = (int)(per_warp * warps);
+  lp.ok = true;
+  return lp;
+}
+
+template <int N, bool FMA>
+int launch_lane(DeviceCtx* ctx, const LanePlan& lp, const LaneParams& P, cudaStream_t st) {
+  auto kern = gi_lane_kernel<N, FMA>;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lane_attr_smem[N][FMA] < lp.smem) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.smem));
+      ctx->lane_attr_smem[N][FMA] = lp.smem;
+    }
+  }
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lp.warps * 32, lp.smem));
+  if (per_sm < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "lane kernel does not fit an SM (smem %d B)", lp.smem);
+  long long ctas = (long long)ctx->sms * per_sm;
+  const long long need = (P.tiles + lp.warps - 1) / lp.warps;
+  if (ctas > need) ctas = need;
+  if (ctas < 1) ctas = 1;
+  kern<<<(unsigned)ctas, lp.warps * 32, lp.smem, st>>>(P);
+  g_launches.fetch_add(1);
+  CU(cudaGetLastError());
+  return MGQP_OK;
+}
+
+template <bool FMA>
+int launch_lane_n(DeviceCtx* ctx, const LanePlan& lp, const LaneParams& P, cudaStream_t st) {
+  switch (lp.v.n) {
+    case 1: return launch_lane<1, FMA>(ctx, lp, P, st);
+    case 2: return launch_lane<2, FMA>(ctx, lp, P, st);
+    case 3: return launch_lane<3, FMA>(ctx, lp, P, st);
+    case 4: return launch_lane<4, FMA>(ctx, lp, P, st);
+    case 5: return launch_lane<5, FMA>(ctx, lp, P, st);
+    case 6: return launch_lane<6, FMA>(ctx, lp, P, st);
+    case 7: return launch_lane<7, FMA>(ctx, lp, P, st);
+    default: return launch_lane<8, FMA>(ctx, lp, P, st);
+  }
+}
+
 int validate(const mgqp_batch* d) {
   if (!d) return fail(MGQP_ERR_INVALID_ARG, "null batch descriptor");
   if (d->n < 1) return fail(MGQP_ERR_INVALID_ARG, "n = %d must be >= 1", d->n);
@@ -151,6 +212,9 @@ int validate(const mgqp_batch* d) {
   if (!d->G || !d->g0 || (d->p && (!d->CE || !d->ce0)) || (d->m && (!d->CI || !d->ci0)))
     return fail(MGQP_ERR_INVALID_ARG, "null input pointer");
   if (!d->x || !d->f || !d->status) return fail(MGQP_ERR_INVALID_ARG, "null output pointer (x, f, status are required)");
+  if (d->p > d->n)
+    return fail(MGQP_ERR_INVALID_ARG, "p = %d equalities on n = %d variables (the reference indexes R out of bounds there)",
+                d->p, d->n);
   if (d->sG < 0 || d->sg0 < 0 || d->sCE < 0 || d->sce0 < 0 || d->sCI < 0 || d->sci0 < 0)
     return fail(MGQP_ERR_INVALID_ARG, "negative stride");
   return MGQP_OK;
@@ -163,6 +227,42 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   DeviceCtx* ctx = nullptr;
   if ((rc = device_ctx(device, &ctx))) return rc;
   CU(cudaSetDevice(device));
+  const int max_iter = d->max_iter > 0 ? d->max_iter : 100 + 10 * (d->p + d->m);
+  unsigned* ticket = nullptr;
+  if (!(d->flags & MGQP_FLAG_STATIC_SCHEDULE)) {
+    unsigned slot;
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      slot = ctx->ring_pos++ % kTicketRing;
+    }
+    ticket = ctx->tickets + slot;
+    CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+  }
+  const bool fast = (d->flags & MGQP_FLAG_FAST_MATH) != 0;
+  if (!(d->flags & MGQP_FLAG_GROUP_KERNEL)) {
+    const LanePlan lp = make_lane_plan(d->n, d->p, d->m, ctx->smem_optin);
+    if (lp.ok) {
+      LaneParams L;
+      memset(&L, 0, sizeof L);
+      L.v = lp.v;
+      L.batch = d->batch;
+      L.tiles = (d->batch + 31) / 32;
+      const double* in[6] = {d->G, d->g0, d->CE, d->ce0, d->CI, d->ci0};
+      const long long stride[6] = {d->sG, d->sg0, d->sCE, d->sce0, d->sCI, d->sci0};
+      const int size[6] = {d->n * d->n, d->n, d->n * d->p, d->p, d->n * d->m, d->m};
+      for (int k = 0; k < 6; k++) {
+        L.in[k] = in[k];
+        L.stride[k] = stride[k];
+        if (size[k] > 0 && stride[k] == size[k] && (32ll * size[k] * 8) % 16 == 0 &&
+            (reinterpret_cast<uintptr_t>(in[k]) % 16) == 0 && !(d->flags & MGQP_FLAG_NO_BULK_COPY))
+          L.prefetch_mask |= 1u << k;
+      }
+      L.x = d->x; L.f = d->f; L.status = d->status; L.iq = d->iq; L.A = d->A; L.iters = d->iters;
+      L.max_iter = max_iter;
+      L.ticket = ticket;
+      return fast ? launch_lane_n<true>(ctx, lp, L, st) : launch_lane_n<false>(ctx, lp, L, st);
+    }
+  }
   const Plan pl = make_plan(d->n, d->p, d->m, ctx->smem_optin);
   if (pl.gw < 0)
     return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "shape n=%d p=%d m=%d is outside the kernels built so far (n <= 32)", d->n,
@@ -199,19 +299,9 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   P.iq = d->iq;
   P.A = d->A;
   P.iters = d->iters;
-  P.max_iter = d->max_iter > 0 ? d->max_iter : 100 + 10 * (d->p + d->m);
+  P.max_iter = max_iter;
   P.bar_bytes = pl.bar_bytes;
-  P.ticket = nullptr;
-  if (!(d->flags & MGQP_FLAG_STATIC_SCHEDULE)) {
-    unsigned slot;
-    {
-      std::lock_guard<std::mutex> lk(ctx->mu);
-      slot = ctx->ring_pos++ % kTicketRing;
-    }
-    P.ticket = ctx->tickets + slot;
-    CU(cudaMemsetAsync(P.ticket, 0, sizeof(unsigned), st));
-  }
-  const bool fast = (d->flags & MGQP_FLAG_FAST_MATH) != 0;
+  P.ticket = ticket;
   const int gi = pl.gw == 8 ? 0 : pl.gw == 16 ? 1 : 2;
   if (pl.gw == 8) return fast ? launch_small<8, true>(ctx, pl, P, st, gi, 1) : launch_small<8, false>(ctx, pl, P, st, gi, 0);
   if (pl.gw == 16) return fast ? launch_small<16, true>(ctx, pl, P, st, gi, 1) : launch_small<16, false>(ctx, pl, P, st, gi, 0);
@@ -435,6 +525,12 @@ int mgqp_device_count(void) {
 int64_t mgqp_kernel_launch_count(void) { return g_launches.load(); }
 
 int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int32_t* warps_per_cta) {
+  const LanePlan lp = make_lane_plan(n, p, m, kSmemBudget);
+  if (lp.ok) {
+    if (smem_bytes_per_cta) *smem_bytes_per_cta = lp.smem;
+    if (warps_per_cta) *warps_per_cta = lp.warps;
+    return 1;
+  }
   const Plan pl = make_plan(n, p, m, kSmemBudget);
   if (smem_bytes_per_cta) *smem_bytes_per_cta = pl.smem;
   if (warps_per_cta) *warps_per_cta = pl.warps;

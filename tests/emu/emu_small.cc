@@ -73,3 +73,60 @@ extern "C" int emu_solve_batch(int n, int p, int m, long long batch, const doubl
   for (auto& t : pool) t.join();
   return 0;
 }
+
+// ------------------------------------------------------------------ lane-per-QP solver (gi_lane.cuh)
+#include "../../motion-generation-using-quadratic-programs_b200/csrc/gi_lane.cuh"
+
+namespace {
+template <int N>
+void lane_one(const LaneView& v, double* S, const LaneIO& io, int max_iter, int fma, double* x, double& f, int& st,
+              int& iq, int& it) {
+  if (fma) gi_lane_solve<N, true>(v, S, io, max_iter, x, f, st, iq, it);
+  else gi_lane_solve<N, false>(v, S, io, max_iter, x, f, st, iq, it);
+}
+}  // namespace
+
+extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const double* G, const double* g0,
+                                    const double* CE, const double* ce0, const double* CI, const double* ci0,
+                                    double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
+                                    int fma) {
+  if (n < 1 || n > 8 || m > 64 || p > n) return -2;
+  const LaneView v = make_lane_view(n, p, m);
+  if (max_iter <= 0) max_iter = 100 + 10 * (p + m);
+  std::vector<double> slot(v.stride);
+  for (long long b = 0; b < batch; b++) {
+    double* S = slot.data();
+    for (int i = 0; i < v.stride; i++) S[i] = -1e300;  // poison
+    int* I = reinterpret_cast<int*>(S + v.oInt);
+    for (int i = 0; i < m; i++) I[v.icidx + i] = LN_EMPTY;
+    const int nm = n * m, CH = 2 * n * n;
+    for (int e0 = 0; e0 < nm; e0 += CH) {
+      const int c = (nm - e0) < CH ? (nm - e0) : CH;
+      for (int off = 0; off < c; off++) S[v.oJ + off] = CI[b * nm + e0 + off];
+      ln_classify(S, v, v.oJ, e0, c);
+    }
+    for (int i = 0; i < n * n; i++) S[v.oR + i] = G[b * n * n + i];
+    for (int i = 0; i < n; i++) S[v.od + i] = g0[b * n + i];
+    for (int i = 0; i < m; i++) S[v.oci0 + i] = ci0[b * m + i];
+    LaneIO io{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI + b * nm, ci0 + b * m};
+    double xo[8];
+    double fo;
+    int st, q, it;
+    switch (n) {
+      case 1: lane_one<1>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      case 2: lane_one<2>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      case 3: lane_one<3>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      case 4: lane_one<4>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      case 5: lane_one<5>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      case 6: lane_one<6>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      case 7: lane_one<7>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+      default: lane_one<8>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
+    }
+    for (int i = 0; i < n; i++) x[b * n + i] = xo[i];
+    f[b] = fo; status[b] = st;
+    if (iq) iq[b] = q;
+    if (iters) iters[b] = it;
+    if (A) for (int i = 0; i < p + m; i++) A[b * (p + m) + i] = (i < q) ? I[v.iA + i] : 0x7fffffff;
+  }
+  return 0;
+}

@@ -1,0 +1,75 @@
+"""CPU: the one-QP-per-lane DEVICE solver body (csrc/gi_lane.cuh, incl. the bound-column
+classification it does while staging CI) compiled for the host, against the oracle: bit-identical
+x, f, verdict, active set and step count."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import default_max_iter
+from helpers import assert_bit_identical
+from mgqp_b200 import workloads
+from test_emu_lockstep import _degenerate_batch
+
+
+def lane_solve(lib, b, max_iter=0, fma=0):
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.emu_lane_solve_batch.restype = C.c_int
+    lib.emu_lane_solve_batch.argtypes = [C.c_int] * 3 + [C.c_longlong] + [dp] * 8 + [ip] * 4 + [C.c_int] * 2
+    B, n, p, m = b.batch, b.n, b.p, b.m
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in b.fields()]
+    x = np.zeros((B, n)); f = np.zeros(B)
+    st = np.zeros(B, np.int32); iq = np.zeros(B, np.int32); A = np.zeros((B, p + m), np.int32); it = np.zeros(B, np.int32)
+    rc = lib.emu_lane_solve_batch(n, p, m, B, *[a.ctypes.data_as(dp) for a in arrs], x.ctypes.data_as(dp),
+                                  f.ctypes.data_as(dp), *[a.ctypes.data_as(ip) for a in (st, iq, A, it)], max_iter, fma)
+    assert rc == 0
+    return dict(x=x, f=f, status=st, iq=iq, A=A, iters=it)
+
+
+def _oracle(restatement, b, max_iter=0):
+    return restatement.solve_batch(b.n, b.p, b.m, *b.fields(), max_iter=max_iter or default_max_iter(b.p, b.m), threads=4)
+
+
+@pytest.mark.parametrize("name,B", [("C2", 3000), ("C5", 3000)])
+def test_headline_shapes(emu_lib, restatement, name, B):
+    b = workloads.make(name, B)
+    assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), name)
+
+
+@pytest.mark.parametrize("box", [False, True])
+@pytest.mark.parametrize("n,p,m", [(5, 2, 12), (8, 0, 20), (8, 3, 9), (3, 1, 0), (7, 0, 0), (1, 0, 3), (2, 1, 3),
+                                   (8, 8, 4), (6, 0, 64), (4, 2, 33)])
+def test_random_shapes_dense_and_bound_columns(emu_lib, restatement, n, p, m, box):
+    b = workloads.make_random(300, n, p, m, seed=n * 100 + m, box=box)
+    assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), f"R{n}_{p}_{m}")
+
+
+def test_degenerate_branch_and_iteration_cap(emu_lib, restatement):
+    b = _degenerate_batch(200)
+    for cap in (7, 60):
+        assert_bit_identical(lane_solve(emu_lib, b, cap), _oracle(restatement, b, cap), f"cap{cap}")
+
+
+def test_failure_verdicts(emu_lib, restatement):
+    b = workloads.make_random(64, 6, 2, 14, seed=11, box=True)
+    b.CE[0::4, :, 1] = -0.5 * b.CE[0::4, :, 0]
+    b.G[1::8] -= 4.0 * np.eye(6)
+    b.ci0[2::8, 0] = -3.0; b.ci0[2::8, 6] = 1.0
+    ref = _oracle(restatement, b)
+    got = lane_solve(emu_lib, b)
+    assert np.array_equal(got["status"], ref["status"])
+    keep = ref["status"] != 2
+    for k in ("x", "iq", "iters", "A"):
+        assert np.array_equal(got[k][keep], ref[k][keep]), k
+    assert np.array_equal(got["f"], ref["f"], equal_nan=True)
+
+
+def test_non_finite_inputs(emu_lib, restatement):
+    b = workloads.make("C2", 2048)
+    b.g0[5::97, 2] = np.inf
+    b.ci0[7::101, 3] = np.nan
+    b.CE[11::103, 1, 0] = np.nan
+    ref = _oracle(restatement, b)
+    got = lane_solve(emu_lib, b)
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["x"], ref["x"], equal_nan=True) and np.array_equal(got["f"], ref["f"], equal_nan=True)

@@ -66,13 +66,18 @@ def test_golden_fixtures_from_reference_binary(gpu, path):
                                    (6, 0, 200), (9, 2, 33), (12, 4, 30), (16, 2, 40), (17, 0, 21), (20, 5, 50),
                                    (32, 4, 70), (31, 31, 5)])
 def test_random_shapes_bit_identical(gpu, restatement, n, p, m):
-    b = workloads.make_random(1003, n, p, m, seed=n * 100 + m)
-    assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), f"R{n}_{p}_{m}")
+    for box in (False, True):   # dense columns (re-read from L2 by the lane kernel) / compressed bound columns
+        b = workloads.make_random(1003, n, p, m, seed=n * 100 + m, box=box)
+        ref = _oracle(restatement, b)
+        assert_bit_identical(_solve(gpu, b), ref, f"R{n}_{p}_{m}")
+        if gpu.plan(n, p, m)[0] == 1:
+            assert_bit_identical(_solve(gpu, b, flags=8), ref, f"R{n}_{p}_{m}/group")
 
 
-@pytest.mark.parametrize("flags", [2, 4, 6])
-def test_staging_and_schedule_variants(gpu, restatement, flags):
-    """NO_BULK_COPY (plain loads instead of TMA) and STATIC_SCHEDULE must not change a bit."""
+@pytest.mark.parametrize("flags", [2, 4, 6, 8, 10, 12, 14])
+def test_staging_schedule_and_kernel_family_variants(gpu, restatement, flags):
+    """NO_BULK_COPY (2), STATIC_SCHEDULE (4) and GROUP_KERNEL (8: lane-group kernel instead of the
+    one-QP-per-lane kernel) must not change a bit."""
     b = workloads.make("C2", 5003)
     assert_bit_identical(_solve(gpu, b, flags=flags), _oracle(restatement, b), f"flags{flags}")
 
@@ -83,13 +88,14 @@ def test_tail_and_tiny_batches(gpu, restatement):
         assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), f"B{B}")
 
 
-def test_failure_verdicts(gpu, restatement):
+@pytest.mark.parametrize("flags", [0, 8])
+def test_failure_verdicts(gpu, restatement, flags):
     b = workloads.make_random(4096, 6, 2, 14, seed=11, box=True)
     b.CE[0::4, :, 1] = -0.5 * b.CE[0::4, :, 0]          # dependent equalities  -> 3
     b.G[1::8] -= 4.0 * np.eye(6)                         # indefinite G          -> 2
     b.ci0[2::8, 0] = -3.0; b.ci0[2::8, 6] = 1.0          # contradictory bounds  -> 1
     ref = _oracle(restatement, b)
-    got = _solve(gpu, b)
+    got = _solve(gpu, b, flags=flags)
     assert set(np.unique(ref["status"])) >= {0, 1, 2, 3}
     assert np.array_equal(got["status"], ref["status"])
     keep = ref["status"] != 2
@@ -98,18 +104,34 @@ def test_failure_verdicts(gpu, restatement):
     assert np.array_equal(got["f"], ref["f"], equal_nan=True)
 
 
-def test_degenerate_branch_and_iteration_cap(gpu, restatement):
+@pytest.mark.parametrize("flags", [0, 8])
+def test_degenerate_branch_and_iteration_cap(gpu, restatement, flags):
     from test_emu_lockstep import _degenerate_batch
     b = _degenerate_batch(2048)
     for cap in (7, 60):
         ref = _oracle(restatement, b, max_iter=cap)
-        assert_bit_identical(_solve(gpu, b, max_iter=cap), ref, f"cap{cap}")
+        assert_bit_identical(_solve(gpu, b, max_iter=cap, flags=flags), ref, f"cap{cap}")
     assert (ref["status"] == 4).any()
 
 
-def test_fast_math_flag_within_tolerance(gpu, restatement):
+@pytest.mark.parametrize("flags", [1, 9])
+def test_fast_math_flag_within_tolerance(gpu, restatement, flags):
     b = workloads.make("C2", 20001)
-    assert_parity(_solve(gpu, b, flags=1), _oracle(restatement, b), "C2/fast")
+    assert_parity(_solve(gpu, b, flags=flags), _oracle(restatement, b), "C2/fast")
+
+
+def test_non_finite_inputs_follow_the_reference(gpu, restatement):
+    """NaN / inf in the data (the reference's own failure mode, '-inf problem.log.txt'): the compressed
+    bound columns must not be used once x stops being finite."""
+    b = workloads.make("C2", 4099)
+    b.g0[5::97, 2] = np.inf
+    b.ci0[7::101, 3] = np.nan
+    b.CE[11::103, 1, 0] = np.nan
+    ref = _oracle(restatement, b)
+    for flags in (0, 8):
+        got = _solve(gpu, b, flags=flags)
+        assert np.array_equal(got["status"], ref["status"])
+        assert np.array_equal(got["x"], ref["x"], equal_nan=True) and np.array_equal(got["f"], ref["f"], equal_nan=True)
 
 
 def test_broadcast_and_padded_strides(gpu, restatement):
