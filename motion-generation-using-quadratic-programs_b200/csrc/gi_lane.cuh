@@ -7,10 +7,10 @@
 //
 // Why a second kernel family: with n = 7 a lane group of 8 (gi_small.cuh) spends most of its issue
 // slots on work that is uniform across the group (divisions, square roots, control) and on ordered
-// cross-lane sums; one lane per QP executes each of those once per QP, about 7x fewer warp
-// instructions per QP (profiles/r01_notes.md).  The price is shared memory: a lane owns a private,
-// bank-skewed slot, so the constraint matrix cannot stay resident in dense form.  Instead each
-// inequality column is classified while it streams in from HBM (its only read):
+// cross-lane sums; one lane per QP executes each of those once per QP.  The price is shared
+// memory: a lane owns a private, bank-skewed slot, so the constraint matrix cannot stay resident
+// in dense form.  Instead each inequality column is classified while it streams in from HBM (its
+// only read):
 //     * at most one nonzero  -> kept as (row, value): joint acceleration / velocity / position /
 //       torque bounds, i.e. every inequality the reference itself ever builds
 //       (src/mgqp.cpp:1080-1128, limitsMatrix = [-I; +I]);
@@ -22,10 +22,15 @@
 // Each lane runs the reference's scalar recurrences in the reference's own operation order, so
 // results are bit-identical to QuadProg++ by construction (no cross-lane arithmetic at all).
 //
-// Slot layout (doubles, lane stride == 1 mod 16 so that the 32 lanes of a warp hit 32 distinct
-// bank pairs whenever they address the same element):
-//   J[N*N] | R[N*N] (G lands here, is factored in place, then becomes R) | x[N] | d[N] | r[N] |
-//   u[N+1] | u_old[N+1] | civ[m] | ci0[m] | ints: A[N+1], A_old[N+1], cidx[m]
+// The set-up (Cholesky of G, J = L^-T, x0 = -G^-1 g0) is fully unrolled over the compile-time N and
+// lives in registers: G and g0 go from global memory straight into registers, only J is written to
+// the slot.  The 49 + 21 + 14 IEEE divisions of that phase are independent across rows, which is
+// where a lone warp per scheduler gets its instruction-level parallelism from.
+//
+// Slot layout (doubles; the lane stride is odd so the 16 lanes of a half warp hit 16 distinct
+// 8-byte bank pairs whenever they address the same element):
+//   J[N*N] | R (upper Hessenberg, packed) | d[N] (doubles as the x mirror during scans) | r[N] |
+//   u[N+1] | u_old[N+1] | civ[m] | ci0[m] | int8: A[N+1], A_old[N+1], cidx[m]
 #pragma once
 #include "warp_prims.cuh"
 
@@ -43,32 +48,38 @@ namespace mgqp {
 
 struct LaneView {
   int n, p, m;
-  int oJ, oR, ox, od, orr, ou, ouold, ociv, oci0, oInt;  // doubles
-  int iA, iAold, icidx;                                   // ints, relative to (int*)(slot + oInt)
-  int stride;                                             // doubles per lane, == 1 (mod 16)
+  int oJ, oR, od, orr, ou, ouold, ociv, oci0, oByte;  // doubles
+  int bA, bAold, bcidx;                                // bytes, relative to (signed char*)(slot + oByte)
+  int stride;                                          // doubles per lane, odd
 };
+
+// R is kept in upper-Hessenberg packed form: row i stores columns >= i-1 (delete_constraint shifts
+// columns left, which puts one entry below the diagonal until the Givens sweep removes it).
+MGQP_HD inline int lane_rh_size(int n) { return (n - 1) * n - ((n - 1) * (n - 2)) / 2 + n; }
+#define MGQP_RH(i, j) ((i) * N - (((i) * ((i)-1)) >> 1) + (j))
 
 MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
   LaneView v;
   v.n = n; v.p = p; v.m = m;
   int o = 0;
   v.oJ = o;     o += n * n;
-  v.oR = o;     o += n * n;
-  v.ox = o;     o += n;
+  v.oR = o;     o += lane_rh_size(n);
   v.od = o;     o += n;
   v.orr = o;    o += n;
   v.ou = o;     o += n + 1;
   v.ouold = o;  o += n + 1;
   v.ociv = o;   o += m;
   v.oci0 = o;   o += m;
-  v.oInt = o;
-  v.iA = 0;
-  v.iAold = n + 1;
-  v.icidx = 2 * (n + 1);
-  const int ints = 2 * (n + 1) + m;
-  o += (ints + 1) / 2;
-  // staging needs room for ceil(n*m/3) raw doubles in J|R
-  while ((o & 15) != 1) o++;
+  v.oByte = o;
+  v.bA = 0;
+  v.bAold = n + 1;
+  v.bcidx = 2 * (n + 1);
+  const int bytes = 2 * (n + 1) + m;
+  o += (bytes + 7) / 8;
+  if ((o & 1) == 0) o++;
+  // odd is enough for conflict-free same-element access; == 1 (mod 16) additionally spreads the
+  // two half warps over disjoint bank pairs
+  while ((o & 15) != 1 && (o & 15) != 9) o += 2;
   v.stride = o;
   return v;
 }
@@ -91,46 +102,22 @@ struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
 };
 
-// Classify `cnt` consecutive raw elements of CI (row-major element index e0 .. e0+cnt) that were
-// staged at S[stage..]: first nonzero of a column -> (row, value); a second one -> DENSE.
-MGQP_DEV void ln_classify(double* S, const LaneView& v, int stage, int e0, int cnt) {
-  int* I = reinterpret_cast<int*>(S + v.oInt);
-  int j = e0 / v.m, i = e0 - j * v.m;
-#pragma unroll 1
-  for (int k = 0; k < cnt; k++) {
-    const double a = S[stage + k];
-    if (a != 0.0) {  // NaN counts as nonzero
-      const int c = I[v.icidx + i];
-      if (c == LN_EMPTY) {
-        I[v.icidx + i] = j;
-        S[v.ociv + i] = a;
-      } else {
-        I[v.icidx + i] = LN_DENSE;
-      }
-    }
-    if (++i == v.m) { i = 0; j++; }
-  }
-}
-
-// The solver proper.  Preconditions: S[oR..] holds G (row-major n*n), S[od..] holds g0,
-// S[oci0..] holds ci0, civ/cidx hold the classified columns.  N == v.n.
 template <int N, bool FMA>
 MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int max_iter, double* x_out,
                             double& f_out, int& status_out, int& iq_out, int& iters_out) {
   const int p = v.p, m = v.m;
   double* J = S + v.oJ;
-  double* R = S + v.oR;  // L during setup
-  double* sx = S + v.ox;
-  double* sd = S + v.od;
+  double* R = S + v.oR;
+  double* sd = S + v.od;  // d; reused as the smem mirror of x while scanning
   double* sr = S + v.orr;
   double* su = S + v.ou;
   double* suold = S + v.ouold;
-  const double* civ = S + v.ociv;
-  const double* sci0 = S + v.oci0;
-  int* I = reinterpret_cast<int*>(S + v.oInt);
-  int* A = I + v.iA;
-  int* Aold = I + v.iAold;
-  const int* cidx = I + v.icidx;
+  double* civ = S + v.ociv;
+  double* sci0 = S + v.oci0;
+  signed char* Bt = reinterpret_cast<signed char*>(S + v.oByte);
+  signed char* A = Bt + v.bA;
+  signed char* Aold = Bt + v.bAold;
+  signed char* cidx = Bt + v.bcidx;
   const double INF = d_inf();
 
   int status = 0, iq = 0, steps = 0;
@@ -139,78 +126,124 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll
   for (int i = 0; i < N; i++) { x[i] = 0.0; z[i] = 0.0; np[i] = 0.0; dd[i] = 0.0; xold[i] = 0.0; }
 
-  // ---------------------------------------------------------------- setup
-  double c1 = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; i++) c1 = d_add(c1, R[i * N + i]);
-
-  bool fail = false;
+  // ---------------------------------------------------------------- inequality columns: classify
+  // Row-major sweep of this QP's CI straight from global memory (each 32-byte sector is fetched from
+  // HBM once and then served by L1 for the lane's next loads); ci0 is parked in the slot.
+  {
 #pragma unroll 1
-  for (int i = 0; i < N && !fail; i++) {
+    for (int i = 0; i < m; i++) {
+      cidx[i] = LN_EMPTY;
+      civ[i] = 0.0;
+    }
 #pragma unroll 1
-    for (int j = i; j < N; j++) {
-      double sum = R[i * N + j];
-#pragma unroll 1
-      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, R[i * N + k], R[j * N + k]);
-      if (i == j) {
-        if (sum <= 0.0) {
-          status = 2;
-          f = sum;
-          fail = true;
-          break;
+    for (int j = 0; j < N; j++) {
+      const double* row = io.CI + j * m;
+#pragma unroll 6
+      for (int i = 0; i < m; i++) {
+        const double a = MGQP_LDG(row + i);
+        if (a != 0.0) {  // NaN counts as nonzero
+          if (cidx[i] == LN_EMPTY) {
+            cidx[i] = (signed char)j;
+            civ[i] = a;
+          } else {
+            cidx[i] = LN_DENSE;
+          }
         }
-        R[i * N + i] = d_sqrt(sum);
-      } else {
-        R[j * N + i] = d_div(sum, R[i * N + i]);
       }
     }
-    if (!fail) {
-#pragma unroll 1
-      for (int k = i + 1; k < N; k++) R[i * N + k] = R[k * N + i];
-    }
+#pragma unroll 6
+    for (int i = 0; i < m; i++) sci0[i] = MGQP_LDG(io.ci0 + i);
   }
 
-  if (!fail) {
+  // ---------------------------------------------------------------- set-up in registers
+  double L[N][N], g0r[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int j = 0; j < N; j++) L[i][j] = MGQP_LDG(io.G + i * N + j);
+    g0r[i] = MGQP_LDG(io.g0 + i);
+  }
+  double c1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) c1 = d_add(c1, L[i][i]);
+
+  bool fail = false;
+  double bad_pivot = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int j = i; j < N; j++) {
+      double sum = L[i][j];
+#pragma unroll
+      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, L[i][k], L[j][k]);
+      if (i == j) {
+        if (!fail && sum <= 0.0) {
+          fail = true;
+          bad_pivot = sum;
+        }
+        L[i][i] = d_sqrt(sum);
+      } else {
+        L[j][i] = d_div(sum, L[i][i]);
+      }
+    }
+#pragma unroll
+    for (int k = i + 1; k < N; k++) L[i][k] = L[k][i];
+  }
+
+  if (fail) {
+    status = 2;
+    f = bad_pivot;
+  } else {
     // J = L^-T (row i = forward_elimination(L, e_i)); c2 = trace(J)
     double c2 = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < N; i++) {
-#pragma unroll 1
-      for (int r = 0; r < N; r++) {
-        double acc = (r == i) ? 1.0 : 0.0;
-#pragma unroll 1
-        for (int j = 0; j < r; j++) acc = msub<FMA>(acc, R[r * N + j], J[i * N + j]);
-        J[i * N + r] = d_div(acc, R[r * N + r]);
-      }
-      c2 = d_add(c2, J[i * N + i]);
-    }
-    // x = -G^-1 g0 ; sd holds g0 on entry, y is built in sr, x in sx
-    sr[0] = d_div(sd[0], R[0]);
-#pragma unroll 1
-    for (int i = 1; i < N; i++) {
-      double a = sd[i];
-#pragma unroll 1
-      for (int j = 0; j < i; j++) a = msub<FMA>(a, R[i * N + j], sr[j]);
-      sr[i] = d_div(a, R[i * N + i]);
-    }
-    sx[N - 1] = d_div(sr[N - 1], R[(N - 1) * N + (N - 1)]);
-#pragma unroll 1
-    for (int i = N - 2; i >= 0; i--) {
-      double a = sr[i];
-#pragma unroll 1
-      for (int j = i + 1; j < N; j++) a = msub<FMA>(a, R[i * N + j], sx[j]);
-      sx[i] = d_div(a, R[i * N + i]);
-    }
-    double fs = 0.0;
+    {
+      double Jr[N][N];
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-      x[i] = -sx[i];
-      fs = mad<FMA>(sd[i], x[i], fs);
+      for (int i = 0; i < N; i++) {
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+          double acc = (r == i) ? 1.0 : 0.0;
+#pragma unroll
+          for (int j = 0; j < r; j++) acc = msub<FMA>(acc, L[r][j], Jr[i][j]);
+          Jr[i][r] = d_div(acc, L[r][r]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        c2 = d_add(c2, Jr[i][i]);
+#pragma unroll
+        for (int r = 0; r < N; r++) J[i * N + r] = Jr[i][r];
+      }
     }
-    f = d_mul(0.5, fs);
-    // L is dead: the block becomes R (all zero)
+    // x = -G^-1 g0 (cholesky_solve: forward then backward elimination), f = 0.5 g0.x
+    {
+      double y[N], xx[N];
+      y[0] = d_div(g0r[0], L[0][0]);
+#pragma unroll
+      for (int i = 1; i < N; i++) {
+        double a = g0r[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) a = msub<FMA>(a, L[i][j], y[j]);
+        y[i] = d_div(a, L[i][i]);
+      }
+      xx[N - 1] = d_div(y[N - 1], L[N - 1][N - 1]);
+#pragma unroll
+      for (int i = N - 2; i >= 0; i--) {
+        double a = y[i];
+#pragma unroll
+        for (int j = i + 1; j < N; j++) a = msub<FMA>(a, L[i][j], xx[j]);
+        xx[i] = d_div(a, L[i][i]);
+      }
+      double fs = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        x[i] = -xx[i];
+        fs = mad<FMA>(g0r[i], x[i], fs);
+      }
+      f = d_mul(0.5, fs);
+    }
 #pragma unroll 1
-    for (int i = 0; i < N * N; i++) R[i] = 0.0;
+    for (int i = 0; i < lane_rh_size(N); i++) R[i] = 0.0;
 
     double R_norm = 1.0;
 
@@ -236,8 +269,8 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       for (int i = iq - 1; i >= 0; i--) {
         double s = 0.0;
 #pragma unroll 1
-        for (int j = i + 1; j < iq; j++) s = mad<FMA>(R[i * N + j], sr[j], s);
-        sr[i] = d_div(d_sub(sd[i], s), R[i * N + i]);
+        for (int j = i + 1; j < iq; j++) s = mad<FMA>(R[MGQP_RH(i, j)], sr[j], s);
+        sr[i] = d_div(d_sub(sd[i], s), R[MGQP_RH(i, i)]);
       }
     };
     auto dot_zz = [&]() {
@@ -287,7 +320,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       }
       iq++;
 #pragma unroll 1
-      for (int i = 0; i < iq; i++) R[i * N + iq - 1] = sd[i];
+      for (int i = 0; i < iq; i++) R[MGQP_RH(i, iq - 1)] = sd[i];
       const double dl = d_abs(sd[iq - 1]);
       if (dl <= d_mul(MGQP_EPS, R_norm)) return false;
       R_norm = (R_norm < dl) ? dl : R_norm;
@@ -307,39 +340,40 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       for (int i = qq; i < iq - 1; i++) {
         A[i] = A[i + 1];
         su[i] = su[i + 1];
-#pragma unroll
-        for (int j = 0; j < N; j++) R[j * N + i] = R[j * N + i + 1];
+        // rows below i+1 are structurally zero in both columns: nothing to move there
+#pragma unroll 1
+        for (int j = 0; j <= i + 1; j++) R[MGQP_RH(j, i)] = R[MGQP_RH(j, i + 1)];
       }
       A[iq - 1] = A[iq];
       su[iq - 1] = su[iq];
       A[iq] = 0;
       su[iq] = 0.0;
 #pragma unroll 1
-      for (int j = 0; j < iq; j++) R[j * N + iq - 1] = 0.0;
+      for (int j = 0; j < iq; j++) R[MGQP_RH(j, iq - 1)] = 0.0;
       iq--;
       if (iq == 0) return;
 #pragma unroll 1
       for (int j = qq; j < iq; j++) {
-        double cc = R[j * N + j], ss = R[(j + 1) * N + j];
+        double cc = R[MGQP_RH(j, j)], ss = R[MGQP_RH(j + 1, j)];
         const double h = ln_distance(cc, ss);
         if (d_abs(h) < MGQP_EPS) continue;
         cc = d_div(cc, h);
         ss = d_div(ss, h);
-        R[(j + 1) * N + j] = 0.0;
+        R[MGQP_RH(j + 1, j)] = 0.0;
         if (cc < 0.0) {
-          R[j * N + j] = -h;
+          R[MGQP_RH(j, j)] = -h;
           cc = -cc;
           ss = -ss;
         } else {
-          R[j * N + j] = h;
+          R[MGQP_RH(j, j)] = h;
         }
         const double xny = d_div(ss, d_add(1.0, cc));
 #pragma unroll 1
         for (int k = j + 1; k < iq; k++) {
-          const double t1 = R[j * N + k], t2 = R[(j + 1) * N + k];
+          const double t1 = R[MGQP_RH(j, k)], t2 = R[MGQP_RH(j + 1, k)];
           const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
-          R[j * N + k] = n1;
-          R[(j + 1) * N + k] = d_sub(d_mul(xny, d_add(t1, n1)), t2);
+          R[MGQP_RH(j, k)] = n1;
+          R[MGQP_RH(j + 1, k)] = d_sub(d_mul(xny, d_add(t1, n1)), t2);
         }
 #pragma unroll
         for (int k = 0; k < N; k++) {
@@ -366,7 +400,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll 1
       for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t2, sr[k]));
       f = d_add(f, d_mul(d_mul(0.5, d_mul(t2, t2)), dot_znp()));
-      A[e] = -e - 1;
+      A[e] = (signed char)(-e - 1);
       if (!add_constraint()) {
         status = 3;
         dead = true;
@@ -391,18 +425,18 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           bool finite = true;
 #pragma unroll
           for (int j = 0; j < N; j++) {
-            sx[j] = x[j];
+            sd[j] = x[j];  // x mirror (d is dead between add_constraint and the next direction())
             finite = finite && (d_abs(x[j]) < INF);
           }
           double psi = 0.0;
-#pragma unroll 1
+          unsigned long long elig = ~act & excl;
+#pragma unroll 3
           for (int i = 0; i < m; i++) {
             const int c = cidx[i];
             double sum;
-            if (c >= 0 && finite) {
-              sum = d_add(0.0, d_mul(civ[i], sx[c]));
-            } else if (c == LN_EMPTY && finite) {
-              sum = 0.0;
+            if (c != LN_DENSE && finite) {
+              // c >= 0: the single nonzero; c == EMPTY: an all-zero column (civ = 0, row 0)
+              sum = d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c]));
             } else {
               sum = 0.0;
 #pragma unroll
@@ -410,11 +444,12 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             }
             sum = d_add(sum, sci0[i]);
             psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
-            if (sum < ss && !((act >> i) & 1ull) && ((excl >> i) & 1ull)) {
+            if (sum < ss && (elig & 1ull)) {
               ss = sum;
               ip = i;
               s_ip = sum;
             }
+            elig >>= 1;
           }
           if (l1) {
             if (d_abs(psi) <= thr) {
@@ -434,14 +469,16 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
               done = true;
             } else {
               const int c = cidx[ip];
+              if (c == LN_DENSE) {
 #pragma unroll
-              for (int j = 0; j < N; j++) {
-                if (c >= 0) np[j] = (j == c) ? civ[ip] : 0.0;
-                else if (c == LN_EMPTY) np[j] = 0.0;
-                else np[j] = MGQP_LDG(io.CI + j * m + ip);
+                for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CI + j * m + ip);
+              } else {
+                const double a = civ[ip];
+#pragma unroll
+                for (int j = 0; j < N; j++) np[j] = (j == c) ? a : 0.0;
               }
               su[iq] = 0.0;
-              A[iq] = ip;
+              A[iq] = (signed char)ip;
               need_scan = false;
             }
           }

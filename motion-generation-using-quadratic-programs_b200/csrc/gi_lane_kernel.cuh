@@ -1,11 +1,11 @@
 // Persistent kernel around gi_lane_solve: every WARP is an independent worker that pulls tiles of
 // 32 consecutive QPs from the atomic work queue; lane q of the warp owns QP q of the tile.
 //
-// Staging (the one HBM read of every input byte) is cooperative and coalesced: the 32 lanes sweep
-// the tile's contiguous [32][n*m] block of CI one QP after the other, parking each chunk in the
-// owner lane's (still unused) J|R area, and every lane then classifies the columns of its own QP
-// from shared memory (gi_lane.cuh).  G, g0 and ci0 take the same route.  The next tile is
-// prefetched into L2 with cp.async.bulk.prefetch while the current one is solved.
+// There is no staging pass: every lane reads its own QP's G, g0, CI and ci0 straight from global
+// memory inside gi_lane_solve (consecutive 8-byte loads of one lane share 32-byte sectors, so HBM
+// sees every byte once and L1 serves the rest); only x goes through shared memory on the way out
+// so that its stores are coalesced.  The next tile is prefetched into L2 with
+// cp.async.bulk.prefetch while the current one is solved.
 #pragma once
 #include "gi_lane.cuh"
 
@@ -24,6 +24,16 @@ struct LaneParams {
 
 __device__ __forceinline__ void lane_prefetch_l2(const void* src, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory");
 }
 
 template <int N, bool FMA>
@@ -66,36 +76,6 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
       }
     }
 
-    // ---- CI: stream through the J|R area in chunks, classify columns
-    int* I = reinterpret_cast<int*>(S + v.oInt);
-    for (int i = 0; i < m; i++) I[v.icidx + i] = LN_EMPTY;
-    const int nm = n * m;
-    const int CH = 2 * n * n;  // J|R are contiguous and free at this point
-    for (int e0 = 0; e0 < nm; e0 += CH) {
-      const int c = (nm - e0) < CH ? (nm - e0) : CH;
-      __syncwarp();
-      for (int q = 0; q < 32; q++) {
-        const long long qq = q0 + (q < cnt ? q : 0);
-        const double* src = P.in[4] + qq * P.stride[4] + e0;
-        double* dst = ws + q * stride + v.oJ;
-        for (int off = lane; off < c; off += 32) dst[off] = __ldg(src + off);
-      }
-      __syncwarp();
-      ln_classify(S, v, v.oJ, e0, c);
-    }
-    __syncwarp();
-    // ---- G -> R area, g0 -> d, ci0
-    for (int q = 0; q < 32; q++) {
-      const long long qq = q0 + (q < cnt ? q : 0);
-      double* Sq = ws + q * stride;
-      const double* g = P.in[0] + qq * P.stride[0];
-      for (int off = lane; off < n * n; off += 32) Sq[v.oR + off] = __ldg(g + off);
-      if (lane < n) Sq[v.od + lane] = __ldg(P.in[1] + qq * P.stride[1] + lane);
-      const double* c0 = P.in[5] + qq * P.stride[5];
-      for (int off = lane; off < m; off += 32) Sq[v.oci0 + off] = __ldg(c0 + off);
-    }
-    __syncwarp();
-
     const long long myq = q0 + (lane < cnt ? lane : 0);
     LaneIO io;
     io.G = P.in[0] + myq * P.stride[0];
@@ -112,11 +92,11 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
 
     // ---- results: x through shared memory so that the global stores are coalesced
 #pragma unroll
-    for (int k = 0; k < N; k++) S[v.ox + k] = xo[k];
+    for (int k = 0; k < N; k++) S[v.od + k] = xo[k];
     __syncwarp();
     for (int e = lane; e < cnt * n; e += 32) {
       const int q = e / n, k = e - q * n;
-      P.x[q0 * n + e] = ws[q * stride + v.ox + k];
+      P.x[q0 * n + e] = ws[q * stride + v.od + k];
     }
     if (lane < cnt) {
       P.f[q0 + lane] = f;
@@ -125,8 +105,8 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
       if (P.iters) P.iters[q0 + lane] = iters;
       if (P.A) {
         int* Ag = P.A + (q0 + lane) * (long long)(p + m);
-        const int* Aq = I + v.iA;
-        for (int i = 0; i < p + m; i++) Ag[i] = (i < iq) ? Aq[i] : 0x7fffffff;
+        const signed char* Aq = reinterpret_cast<const signed char*>(S + v.oByte) + v.bA;
+        for (int i = 0; i < p + m; i++) Ag[i] = (i < iq) ? (int)Aq[i] : 0x7fffffff;
       }
     }
     __syncwarp();

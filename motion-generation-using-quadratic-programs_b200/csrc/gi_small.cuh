@@ -94,7 +94,7 @@ MGQP_DEV double gi_distance(double a, double b) {
 // One Givens rotation's coefficients from (cc, ss) as add_constraint / delete_constraint derive
 // them.  Returns false when the reference `continue`s (|h| < eps).  diag = the value the pivot
 // entry takes (+-h).
-MGQP_DEV bool gi_givens(double& cc, double& ss, double& xny, double& diag) {
+MGQP_DEV_NOINLINE bool gi_givens(double& cc, double& ss, double& xny, double& diag) {
   const double h = gi_distance(cc, ss);
   if (d_abs(h) < MGQP_EPS) return false;
   ss = d_div(ss, h);
@@ -140,6 +140,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (in_n) sred[li] = v;
     wp_sync();
     double acc = 0.0;
+    MGQP_UNROLL1
     for (int i = 0; i < n; i++) acc = d_add(acc, sred[i]);
     wp_sync();
     return acc;
@@ -151,16 +152,21 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
 
   // ------------------------------------------------------------------ setup (Appendix A, top)
   double c1 = 0.0;
+  MGQP_UNROLL1
   for (int i = 0; i < n; i++) c1 = d_add(c1, sG[i * n + i]);
-  if (in_n)
+  if (in_n) {
+    MGQP_UNROLL1
     for (int j = 0; j < n; j++) sR[li * ldR + j] = 0.0;
+  }
 
   // Cholesky, row-oriented as the reference: lane j owns entry (i, j) of row i
+  MGQP_UNROLL1
   for (int i = 0; i < n; i++) {
     const bool act = in_n && li >= i;
     double sum = 0.0;
     if (act) {
       sum = sG[i * n + li];
+      MGQP_UNROLL1
       for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sG[i * n + k], sG[li * n + k]);
     }
     const double piv = wp_shfl(sum, i, GW);
@@ -184,14 +190,17 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
 
   // J = L^-T: lane i runs forward_elimination(L, e_i) and keeps the result as row i of J
   if (in_n) {
+    MGQP_UNROLL1
     for (int r = 0; r < n; r++) {
       double acc = (r == li) ? 1.0 : 0.0;
+      MGQP_UNROLL1
       for (int j = 0; j < r; j++) acc = msub<FMA>(acc, sG[r * n + j], sJ[li * ldJ + j]);
       sJ[li * ldJ + r] = d_div(acc, sG[r * n + r]);
     }
   }
   wp_sync();
   double c2 = 0.0;
+  MGQP_UNROLL1
   for (int i = 0; i < n; i++) c2 = d_add(c2, sJ[i * ldJ + i]);
 
   // x = -G^-1 g0 : forward elimination across lanes (lane i accumulates row i; the subtraction
@@ -200,6 +209,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   double xv = 0.0;
   {
     double acc = in_n ? sg0[li] : 0.0, yv = 0.0;
+    MGQP_UNROLL1
     for (int j = 0; j < n; j++) {
       const double q = d_div(acc, sG[j * n + j]);
       const double yj = wp_shfl(q, j, GW);
@@ -208,8 +218,10 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     }
     if (in_n) sd[li] = yv;
     wp_sync();
+    MGQP_UNROLL1
     for (int i = n - 1; i >= 0; i--) {
       double a = sd[i];
+      MGQP_UNROLL1
       for (int j = i + 1; j < n; j++) a = msub<FMA>(a, sG[i * n + j], sx[j]);
       a = d_div(a, sG[i * n + i]);
       sx[i] = a;  // every lane of the group stores the same value
@@ -219,6 +231,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (in_n) sx[li] = xv;
     wp_sync();
     double fs = 0.0;
+    MGQP_UNROLL1
     for (int i = 0; i < n; i++) fs = mad<FMA>(sg0[i], sx[i], fs);
     if (!done) f = d_mul(0.5, fs);
   }
@@ -238,16 +251,22 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   auto direction = [&](const double* npp, int nps) {
     dv = 0.0;
     npv = in_n ? npp[li * nps] : 0.0;
-    if (in_n)
+    if (in_n) {
+      MGQP_UNROLL1
       for (int j = 0; j < n; j++) dv = mad<FMA>(sJ[j * ldJ + li], npp[j * nps], dv);
+    }
     if (in_n) sd[li] = dv;
     wp_sync();
     zv = 0.0;
-    if (in_n)
+    if (in_n) {
+      MGQP_UNROLL1
       for (int j = iq; j < n; j++) zv = mad<FMA>(sJ[li * ldJ + j], sd[j], zv);
+    }
     rv = 0.0;
+    MGQP_UNROLL1
     for (int i = iq - 1; i >= 0; i--) {
       double sum = 0.0;
+      MGQP_UNROLL1
       for (int j = i + 1; j < iq; j++) sum = mad<FMA>(sR[i * ldR + j], sr[j], sum);
       const double ri = d_div(d_sub(sd[i], sum), sR[i * ldR + i]);
       sr[i] = ri;  // same value from every lane of the group
@@ -261,6 +280,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     const int jlo = doit ? iq + 1 : n;
     const int jmin = wp_min(jlo);
     double carry = (n > 0) ? sd[n - 1] : 0.0;  // current value of d[j]
+    MGQP_UNROLL1
     for (int j = n - 1; j >= jmin; j--) {
       if (j >= jlo) {
         double cc = sd[j - 1], ss = carry, xny = 0.0, diag = 0.0;
@@ -312,6 +332,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
         uv = uq;
       }
       if (in_n) {
+        MGQP_UNROLL1
         for (int i = qq; i < iq - 1; i++) sR[li * ldR + i] = sR[li * ldR + i + 1];
         if (li < iq) sR[li * ldR + iq - 1] = 0.0;
       }
@@ -320,6 +341,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     const int len = (doit && iq > 0) ? (iq - qq) : 0;
     const int lmax = wp_max(len);
     wp_sync();
+    MGQP_UNROLL1
     for (int t = 0; t < lmax; t++) {
       const int j = qq + t;
       bool rot = false;
@@ -353,6 +375,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   };
 
   // ------------------------------------------------------------------ equality constraints
+  MGQP_UNROLL1
   for (int e = 0; e < p; e++) {
     direction(sCE + e, p);
     const double zz = osum(d_mul(zv, zv));
@@ -392,6 +415,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   double x_old = 0.0, u_old = 0.0;
   int A_old = 0;
 
+  MGQP_UNROLL1
   while (wp_any(!done)) {
     // ---------------- step 1 / step 2: violated-constraint scan and choice of ip
     if (wp_any(!done && need_scan)) {
@@ -403,10 +427,12 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       }
       double best = ss, psi = 0.0;
       int bidx = NONE;
+      MGQP_UNROLL1
       for (int k = 0; k < nk; k++) {
         const int i = li + (k << LOGG);
         if (i < m) {
           double sum = 0.0;
+          MGQP_UNROLL1
           for (int j = 0; j < n; j++) sum = mad<FMA>(sCI[j * m + i], sx[j], sum);
           sum = d_add(sum, sci0[i]);
           if (sum < 0.0) psi = d_add(psi, sum);
@@ -416,6 +442,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
           }
         }
       }
+      MGQP_UNROLL1
       for (int off = GW >> 1; off > 0; off >>= 1) {
         const double ov = wp_shfl_xor(best, off, GW);
         const int oi = wp_shfl_xor(bidx, off, GW);
@@ -430,8 +457,10 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
           if (!FMA && d_abs(psi) > d_mul(0.5, thr) && d_abs(psi) < d_mul(2.0, thr)) {
             // within 2x of the threshold: redo the sum in the reference's order (rare)
             psi = 0.0;
+            MGQP_UNROLL1
             for (int i = 0; i < m; i++) {
               double sum = 0.0;
+              MGQP_UNROLL1
               for (int j = 0; j < n; j++) sum = mad<FMA>(sCI[j * m + i], sx[j], sum);
               sum = d_add(sum, sci0[i]);
               psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
@@ -480,6 +509,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       if (!(ratio < INF)) ratio = INF;  // NaN / inf never win `u/r < t1`
     }
     int lk = (ratio < INF) ? li : NONE;
+    MGQP_UNROLL1
     for (int off = GW >> 1; off > 0; off >>= 1) {
       const double ov = wp_shfl_xor(ratio, off, GW);
       const int oi = wp_shfl_xor(lk, off, GW);
@@ -567,6 +597,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
         }
         xv = x_old;
       }
+      MGQP_UNROLL1
       for (int k = 0; k < n; k++) {  // iai[A[i]] = -1 for i in [p, iq)
         const int a = wp_shfl(Av, k, GW);
         if (degenerate && k >= p && k < iq && li == (a & (GW - 1))) act_mask |= (1u << (a >> LOGG));
@@ -596,6 +627,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     }
     if (out.A) {
       int* Ag = out.A + (long long)g * (p + m);
+      MGQP_UNROLL1
       for (int i = li; i < p + m; i += GW) Ag[i] = (i < iq) ? Av : NONE;  // i < iq <= n implies i == li
     }
   }

@@ -101,17 +101,18 @@ __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant_
     // ---- stage the tile
     if (bulk && lane == 0) {
       mbar_expect_tx(bar, P.bulk_bytes);
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 6; k++)
         if (bulk & (1u << k))
           bulk_g2s(ws + P.off[k], P.in[k] + q0 * P.stride[k], (unsigned)(QPW * P.size[k] * 8), bar);
     }
     // fields that cannot go through TMA (odd alignment, broadcast or padded strides, tail tile):
     // plain coalesced loads; groups beyond the tail replicate the tile's first QP
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {  // cold path: keep it small (instruction-cache footprint)
       if (!(bulk & (1u << k)) && P.size[k] > 0) {
         const int sz = P.size[k], tot = QPW * sz;
+#pragma unroll 1
         for (int idx = lane; idx < tot; idx += 32) {
           const int q = idx / sz, e = idx - q * sz;
           const long long qq = q0 + (q < cnt ? q : 0);

@@ -97,18 +97,7 @@ extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const 
   for (long long b = 0; b < batch; b++) {
     double* S = slot.data();
     for (int i = 0; i < v.stride; i++) S[i] = -1e300;  // poison
-    int* I = reinterpret_cast<int*>(S + v.oInt);
-    for (int i = 0; i < m; i++) I[v.icidx + i] = LN_EMPTY;
-    const int nm = n * m, CH = 2 * n * n;
-    for (int e0 = 0; e0 < nm; e0 += CH) {
-      const int c = (nm - e0) < CH ? (nm - e0) : CH;
-      for (int off = 0; off < c; off++) S[v.oJ + off] = CI[b * nm + e0 + off];
-      ln_classify(S, v, v.oJ, e0, c);
-    }
-    for (int i = 0; i < n * n; i++) S[v.oR + i] = G[b * n * n + i];
-    for (int i = 0; i < n; i++) S[v.od + i] = g0[b * n + i];
-    for (int i = 0; i < m; i++) S[v.oci0 + i] = ci0[b * m + i];
-    LaneIO io{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI + b * nm, ci0 + b * m};
+    LaneIO io{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI + b * n * m, ci0 + b * m};
     double xo[8];
     double fo;
     int st, q, it;
@@ -126,7 +115,8 @@ extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const 
     f[b] = fo; status[b] = st;
     if (iq) iq[b] = q;
     if (iters) iters[b] = it;
-    if (A) for (int i = 0; i < p + m; i++) A[b * (p + m) + i] = (i < q) ? I[v.iA + i] : 0x7fffffff;
+    const signed char* Ab = reinterpret_cast<const signed char*>(S + v.oByte) + v.bA;
+    if (A) for (int i = 0; i < p + m; i++) A[b * (p + m) + i] = (i < q) ? (int)Ab[i] : 0x7fffffff;
   }
   return 0;
 }
