@@ -40,8 +40,10 @@
 
 #ifdef MGQP_EMULATE
 #define MGQP_LDG(p) (*(p))
+#define MGQP_LDG2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
 #else
 #define MGQP_LDG(p) __ldg(p)
+#define MGQP_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
 #endif
 
 namespace mgqp {
@@ -135,20 +137,36 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       cidx[i] = LN_EMPTY;
       civ[i] = 0.0;
     }
-#pragma unroll 1
-    for (int j = 0; j < N; j++) {
-      const double* row = io.CI + j * m;
-#pragma unroll 6
-      for (int i = 0; i < m; i++) {
-        const double a = MGQP_LDG(row + i);
-        if (a != 0.0) {  // NaN counts as nonzero
-          if (cidx[i] == LN_EMPTY) {
-            cidx[i] = (signed char)j;
-            civ[i] = a;
-          } else {
-            cidx[i] = LN_DENSE;
-          }
+    auto classify = [&](double a, int j, int i) {
+      if (a != 0.0) {  // NaN counts as nonzero
+        if (cidx[i] == LN_EMPTY) {
+          cidx[i] = (signed char)j;
+          civ[i] = a;
+        } else {
+          cidx[i] = LN_DENSE;
         }
+      }
+    };
+    const int nm = N * m;
+    if (((nm & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.CI) & 15ull) == 0ull)) {
+      // 16-byte loads, 8 in flight: a 32-byte sector is consumed by two back-to-back loads of the
+      // same lane instead of living in L1 across loop iterations
+      int j = 0, i = 0;
+#pragma unroll 8
+      for (int e = 0; e < nm; e += 2) {
+        double a0, a1;
+        MGQP_LDG2(io.CI + e, a0, a1);
+        classify(a0, j, i);
+        if (++i == m) { i = 0; j++; }
+        classify(a1, j, i);
+        if (++i == m) { i = 0; j++; }
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < N; j++) {
+        const double* row = io.CI + j * m;
+#pragma unroll 6
+        for (int i = 0; i < m; i++) classify(MGQP_LDG(row + i), j, i);
       }
     }
 #pragma unroll 6
@@ -430,6 +448,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           }
           double psi = 0.0;
           unsigned long long elig = ~act & excl;
+          bool picked = false;
 #pragma unroll 3
           for (int i = 0; i < m; i++) {
             const int c = cidx[i];
@@ -447,10 +466,11 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             if (sum < ss && (elig & 1ull)) {
               ss = sum;
               ip = i;
-              s_ip = sum;
+              picked = true;
             }
             elig >>= 1;
           }
+          if (picked) s_ip = ss;
           if (l1) {
             if (d_abs(psi) <= thr) {
               done = true;
