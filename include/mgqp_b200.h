@@ -65,7 +65,9 @@ enum {
   MGQP_FLAG_STATIC_SCHEDULE = 4,
   /* Always use the lane-group kernel (8/16/32 lanes per QP), even where the one-QP-per-lane
    * kernel (n <= 8, m <= 64) would be picked. */
-  MGQP_FLAG_GROUP_KERNEL = 8
+  MGQP_FLAG_GROUP_KERNEL = 8,
+  /* Always use the CTA-per-QP kernel (the one that serves n > 32). */
+  MGQP_FLAG_CTA_KERNEL = 16
 };
 
 /* One batch of `batch` independent QPs of one shape, field-wise SoA, DEVICE pointers.

@@ -27,13 +27,15 @@ import numpy as np
 __all__ = [
     "LogicError", "QPResult", "STATUS", "lib", "lib_path", "solve_quadprog", "solve_quadprog_batched",
     "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
-    "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "mgqp_batch",
+    "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL", "mgqp_batch",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FLAG_FAST_MATH = 1
 FLAG_NO_BULK_COPY = 2
 FLAG_STATIC_SCHEDULE = 4
+FLAG_GROUP_KERNEL = 8
+FLAG_CTA_KERNEL = 16
 STATUS = {0: "ok", 1: "infeasible", 2: "not_pd", 3: "eq_dependent", 4: "iter_cap"}
 
 

@@ -1,0 +1,704 @@
+// Goldfarb-Idnani dual active-set solver, ONE QP PER CTA (n > 32, or m too large for the warp
+// kernels): the horizon-stacked shapes (BASELINE.json configs[3]: n = 350, m = 2100).
+//
+// Replaces the body of the reference's solve_quadprog (lib/QuadProgpp/libquadprog.a: QuadProg++.o;
+// prototype include/QuadProgpp/QuadProg++.hh:69-72; spec SURVEY.md Appendix A).  At this size the
+// matrices no longer fit on chip: the Cholesky factor, J and R (n*n doubles each) live in a per-CTA
+// global-memory workspace that stays L2-resident between uses, the vectors and the per-rotation
+// Givens coefficients live in shared memory, and CE/CI are read in place (CI once per
+// violated-constraint scan, which is what bounds this kernel: 8*n*m bytes per iteration).
+//
+// Parallel decomposition (T threads, every reduction order is the reference's):
+//   * every dot product of length n is owned by ONE thread and accumulated in ascending index
+//     order, one rounding per operation: the threads split the OUTPUT index (column i of the scan,
+//     element i of d = J^T np and z = J d), never the summation index;
+//   * add_constraint's Givens sweep is split in three: a serial chain that only produces the
+//     hypotenuses h_j (`distance` ignores the sign of its arguments, so the chain needs nothing
+//     else), one parallel pass that turns them into (c, s, s/(1+c)) with the reference's sign
+//     normalisation, and a row-parallel pass in which each thread streams its own rows of J right to
+//     left through all rotations -- no barrier between rotations;
+//   * the triangular solves whose subtraction order is the reverse of data availability
+//     (backward_elimination, update_r) are left to one thread.
+// Control flow is uniform across the CTA: thread 0's decisions are broadcast through shared memory.
+#pragma once
+#include "gi_lane.cuh"  // LaneIO, ln_distance, MGQP_LDG, MGQP_EPS
+
+namespace mgqp {
+
+struct LargeView {
+  int n, p, m, T;
+  // shared memory, in doubles from the (16-byte aligned) base
+  int ox, oz, od, onp, orr, ou, oxold, ouold, oh, occ, oss, oxny, ored, obc;
+  int oredi, oA, oAold;   // ints, byte offsets
+  int oact, oexcl, oskip; // bytes, byte offsets
+  int smem_bytes;
+  long long ws_doubles;   // global workspace per CTA: Gc | J | R | s
+};
+
+MGQP_HOST inline LargeView make_large_view(int n, int p, int m, int T) {
+  LargeView v;
+  v.n = n; v.p = p; v.m = m; v.T = T;
+  int o = 0;
+  v.ox = o; o += n;
+  v.oz = o; o += n;
+  v.od = o; o += n;
+  v.onp = o; o += n;
+  v.orr = o; o += n + 1;
+  v.ou = o; o += n + 1;
+  v.oxold = o; o += n;
+  v.ouold = o; o += n + 1;
+  v.oh = o; o += n + 1;
+  v.occ = o; o += n + 1;
+  v.oss = o; o += n + 1;
+  v.oxny = o; o += n + 1;
+  v.ored = o; o += T;
+  v.obc = o; o += 16;
+  int b = o * 8;
+  v.oredi = b; b += 4 * T;
+  v.oA = b; b += 4 * (n + 2);
+  v.oAold = b; b += 4 * (n + 2);
+  v.oact = b; b += m;
+  v.oexcl = b; b += m;
+  v.oskip = b; b += n + 1;
+  v.smem_bytes = (b + 15) & ~15;
+  v.ws_doubles = 3ll * n * n + m;
+  return v;
+}
+
+struct LargeOut {
+  double* x; double* f; int* status; int* iq; int* A; int* iters;
+};
+
+template <bool FMA>
+MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws, const LaneIO& io, int max_iter,
+                             const LargeOut& out) {
+  const int n = v.n, p = v.p, m = v.m;
+  const int tid = blk_tid(), T = blk_dim();
+  double* sm = reinterpret_cast<double*>(smem);
+  double* sx = sm + v.ox;
+  double* sz = sm + v.oz;
+  double* sd = sm + v.od;
+  double* snp = sm + v.onp;
+  double* sr = sm + v.orr;
+  double* su = sm + v.ou;
+  double* sxold = sm + v.oxold;
+  double* suold = sm + v.ouold;
+  double* sh = sm + v.oh;      // hypotenuse per rotation; also scratch
+  double* scc = sm + v.occ;
+  double* sss = sm + v.oss;
+  double* sxny = sm + v.oxny;
+  double* sred = sm + v.ored;
+  double* sbc = sm + v.obc;    // broadcast slots
+  int* sredi = reinterpret_cast<int*>(smem + v.oredi);
+  int* A = reinterpret_cast<int*>(smem + v.oA);
+  int* Aold = reinterpret_cast<int*>(smem + v.oAold);
+  unsigned char* act = smem + v.oact;    // iai[i] == -1
+  unsigned char* excl = smem + v.oexcl;  // iaexcl[i]
+  unsigned char* skip = smem + v.oskip;  // rotation j skipped (|h| < eps)
+  double* Gc = ws;
+  double* J = Gc + (size_t)n * n;
+  double* R = J + (size_t)n * n;
+  double* sg = R + (size_t)n * n;  // s[m], only read back on the rare exact-psi path
+  const double INF = d_inf();
+  constexpr int NONE = 0x7fffffff;
+
+  // lexicographic (value, index) minimum over the block; every thread gets the result
+  auto block_argmin = [&](double val, int idx, double& oval, int& oidx) {
+    sred[tid] = val;
+    sredi[tid] = idx;
+    blk_sync();
+    MGQP_UNROLL1
+    for (int s = T >> 1; s > 0; s >>= 1) {
+      if (tid < s) {
+        const double a = sred[tid + s];
+        const int ai = sredi[tid + s];
+        if (a < sred[tid] || (a == sred[tid] && ai < sredi[tid])) {
+          sred[tid] = a;
+          sredi[tid] = ai;
+        }
+      }
+      blk_sync();
+    }
+    oval = sred[0];
+    oidx = sredi[0];
+    blk_sync();
+  };
+  auto block_sum = [&](double val) -> double {
+    sred[tid] = val;
+    blk_sync();
+    MGQP_UNROLL1
+    for (int s = T >> 1; s > 0; s >>= 1) {
+      if (tid < s) sred[tid] = d_add(sred[tid], sred[tid + s]);
+      blk_sync();
+    }
+    const double r = sred[0];
+    blk_sync();
+    return r;
+  };
+  // ascending-order dot product of two shared vectors, done by thread 0 and broadcast
+  auto dot0 = [&](const double* a, const double* b, int slot) {
+    if (tid == 0) {
+      double s = 0.0;
+      MGQP_UNROLL1
+      for (int i = 0; i < n; i++) s = mad<FMA>(a[i], b[i], s);
+      sbc[slot] = s;
+    }
+  };
+
+  int status = 0, iq = 0, steps = 0;
+  double f = 0.0;
+
+  // ---------------------------------------------------------------- set-up
+  MGQP_UNROLL1
+  for (int e = tid; e < n * n; e += T) Gc[e] = MGQP_LDG(io.G + e);
+  MGQP_UNROLL1
+  for (int e = tid; e < n * n; e += T) R[e] = 0.0;
+  blk_sync();
+  if (tid == 0) {
+    double c = 0.0;
+    MGQP_UNROLL1
+    for (int i = 0; i < n; i++) c = d_add(c, Gc[(size_t)i * n + i]);
+    sbc[0] = c;
+  }
+  blk_sync();
+  const double c1 = sbc[0];
+  blk_sync();
+
+  // Cholesky, row-oriented as the reference; row i is staged in sz for the broadcast operand
+  bool fail = false;
+  MGQP_UNROLL1
+  for (int i = 0; i < n && !fail; i++) {
+    MGQP_UNROLL1
+    for (int k = tid; k < i; k += T) sz[k] = Gc[(size_t)i * n + k];
+    blk_sync();
+    MGQP_UNROLL1
+    for (int j = i + tid; j < n; j += T) {
+      double sum = Gc[(size_t)i * n + j];
+      const double* rowj = Gc + (size_t)j * n;
+      MGQP_UNROLL1
+      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sz[k], rowj[k]);
+      sd[j] = sum;
+    }
+    blk_sync();
+    const double piv = sd[i];
+    if (piv <= 0.0) {
+      fail = true;
+      status = 2;
+      f = piv;
+    } else {
+      const double dii = d_sqrt(piv);
+      MGQP_UNROLL1
+      for (int j = i + tid; j < n; j += T) {
+        if (j == i) {
+          Gc[(size_t)i * n + i] = dii;
+        } else {
+          const double val = d_div(sd[j], dii);
+          Gc[(size_t)j * n + i] = val;
+          Gc[(size_t)i * n + j] = val;
+        }
+      }
+    }
+    blk_sync();
+  }
+
+  double c2 = 0.0, R_norm = 1.0;
+  if (!fail) {
+    // J = L^-T: thread i owns row i = forward_elimination(L, e_i)
+    MGQP_UNROLL1
+    for (int i = tid; i < n; i += T) {
+      double* Ji = J + (size_t)i * n;
+      MGQP_UNROLL1
+      for (int r = 0; r < n; r++) {
+        double acc = (r == i) ? 1.0 : 0.0;
+        const double* Lr = Gc + (size_t)r * n;
+        MGQP_UNROLL1
+        for (int j = 0; j < r; j++) acc = msub<FMA>(acc, Lr[j], Ji[j]);
+        Ji[r] = d_div(acc, Lr[r]);
+      }
+    }
+    blk_sync();
+    // forward elimination for x0 across threads (subtraction order j = 0,1,.. = availability order)
+    MGQP_UNROLL1
+    for (int i = tid; i < n; i += T) sd[i] = MGQP_LDG(io.g0 + i);
+    blk_sync();
+    MGQP_UNROLL1
+    for (int j = 0; j < n; j++) {
+      if (tid == 0) sz[j] = d_div(sd[j], Gc[(size_t)j * n + j]);
+      blk_sync();
+      const double yj = sz[j];
+      MGQP_UNROLL1
+      for (int i = j + 1 + tid; i < n; i += T) sd[i] = msub<FMA>(sd[i], Gc[(size_t)i * n + j], yj);
+      blk_sync();
+    }
+    // backward elimination, c2, f: serial (ascending-j subtraction is the reverse of availability)
+    if (tid == 0) {
+      MGQP_UNROLL1
+      for (int i = n - 1; i >= 0; i--) {
+        double a = sz[i];
+        const double* Ui = Gc + (size_t)i * n;
+        MGQP_UNROLL1
+        for (int j = i + 1; j < n; j++) a = msub<FMA>(a, Ui[j], sx[j]);
+        sx[i] = d_div(a, Ui[i]);
+      }
+      double t = 0.0, fs = 0.0;
+      MGQP_UNROLL1
+      for (int i = 0; i < n; i++) {
+        t = d_add(t, J[(size_t)i * n + i]);
+        sx[i] = -sx[i];
+        fs = mad<FMA>(MGQP_LDG(io.g0 + i), sx[i], fs);
+      }
+      sbc[0] = t;
+      sbc[1] = d_mul(0.5, fs);
+    }
+    blk_sync();
+    c2 = sbc[0];
+    f = sbc[1];
+    blk_sync();
+  }
+
+  // d = J^T np ; z = J[:, iq:] d[iq:] ; r = R[0:iq,0:iq]^-1 d[0:iq]
+  auto direction = [&]() {
+    MGQP_UNROLL1
+    for (int i = tid; i < n; i += T) {
+      double s = 0.0;
+      MGQP_UNROLL1
+      for (int j = 0; j < n; j++) s = mad<FMA>(J[(size_t)j * n + i], snp[j], s);
+      sd[i] = s;
+    }
+    blk_sync();
+    MGQP_UNROLL1
+    for (int i = tid; i < n; i += T) {
+      double s = 0.0;
+      const double* Ji = J + (size_t)i * n;
+      MGQP_UNROLL1
+      for (int j = iq; j < n; j++) s = mad<FMA>(Ji[j], sd[j], s);
+      sz[i] = s;
+    }
+    if (tid == 0) {
+      MGQP_UNROLL1
+      for (int i = iq - 1; i >= 0; i--) {
+        double s = 0.0;
+        const double* Ri = R + (size_t)i * n;
+        MGQP_UNROLL1
+        for (int j = i + 1; j < iq; j++) s = mad<FMA>(Ri[j], sr[j], s);
+        sr[i] = d_div(d_sub(sd[i], s), Ri[i]);
+      }
+    }
+    blk_sync();
+  };
+
+  // add_constraint (Appendix A).  Returns the reference's bool; iq is incremented.
+  auto add_constraint = [&]() -> bool {
+    // (1) serial chain: hypotenuses only.  sh[j] = h of rotation j, skip[j] = |h| < eps.
+    if (tid == 0) {
+      double carry = (n > 0) ? d_abs(sd[n - 1]) : 0.0;  // |current d[j]|
+      MGQP_UNROLL1
+      for (int j = n - 1; j >= iq + 1; j--) {
+        const double h = ln_distance(sd[j - 1], carry);
+        if (d_abs(h) < MGQP_EPS) {
+          skip[j] = 1;
+          carry = d_abs(sd[j - 1]);
+        } else {
+          skip[j] = 0;
+          sh[j] = h;
+          carry = h;
+        }
+      }
+    }
+    blk_sync();
+    // (2a) normalised cosine and the signed value each rotation leaves in d[j-1]
+    MGQP_UNROLL1
+    for (int j = iq + 1 + tid; j <= n - 1; j += T) {
+      if (!skip[j]) {
+        const double c = d_div(sd[j - 1], sh[j]);
+        scc[j] = c;
+        sxny[j] = (c < 0.0) ? -sh[j] : sh[j];  // new d[j-1] (parked in sxny until pass 2b)
+      } else {
+        sxny[j] = sd[j - 1];
+      }
+    }
+    blk_sync();
+    // (2b) sine, sign normalisation, s/(1+c).  Rotation j's incoming d[j] is what rotation j+1 left.
+    MGQP_UNROLL1
+    for (int j = iq + 1 + tid; j <= n - 1; j += T) {
+      if (!skip[j]) {
+        const double din = (j == n - 1) ? sd[n - 1] : sxny[j + 1];
+        double s = d_div(din, sh[j]);
+        double c = scc[j];
+        if (c < 0.0) {
+          c = -c;
+          s = -s;
+        }
+        scc[j] = c;
+        sss[j] = s;
+        sh[j] = d_div(s, d_add(1.0, c));  // xny; h itself is no longer needed
+      }
+    }
+    blk_sync();
+    // d[iq] after the sweep: what rotation iq+1 left there, or the untouched entry if there was none
+    const double dlast = (iq + 1 <= n - 1) ? sxny[iq + 1] : sd[iq];
+    // (3) every thread streams its rows of J right to left through all rotations
+    MGQP_UNROLL1
+    for (int k = tid; k < n; k += T) {
+      double* Jk = J + (size_t)k * n;
+      double t2 = Jk[n - 1];
+      MGQP_UNROLL1
+      for (int j = n - 1; j >= iq + 1; j--) {
+        const double t1 = Jk[j - 1];
+        if (!skip[j]) {
+          const double n1 = d_add(d_mul(t1, scc[j]), d_mul(t2, sss[j]));
+          Jk[j] = d_sub(d_mul(sh[j], d_add(t1, n1)), t2);
+          t2 = n1;
+        } else {
+          Jk[j] = t2;
+          t2 = t1;
+        }
+      }
+      if (iq + 1 <= n - 1) Jk[iq] = t2;
+    }
+    // column iq of R <- d[0..iq]
+    MGQP_UNROLL1
+    for (int i = tid; i < iq; i += T) R[(size_t)i * n + iq] = sd[i];
+    if (tid == 0) R[(size_t)iq * n + iq] = dlast;
+    iq++;
+    blk_sync();
+    if (d_abs(dlast) <= d_mul(MGQP_EPS, R_norm)) return false;
+    R_norm = (R_norm < d_abs(dlast)) ? d_abs(dlast) : R_norm;
+    return true;
+  };
+
+  // delete_constraint(l); the pending pair (A[iq], u[iq]) sits at index iq of A / su
+  auto delete_constraint = [&](int l) {
+    if (tid == 0) {
+      int qq = 0;
+      MGQP_UNROLL1
+      for (int i = p; i < iq; i++)
+        if (A[i] == l) {
+          qq = i;
+          break;
+        }
+      sredi[0] = qq;
+    }
+    blk_sync();
+    const int qq = sredi[0];
+    blk_sync();
+    // shift columns qq+1.. of R one to the left (row-parallel), A and u likewise
+    MGQP_UNROLL1
+    for (int j = tid; j < n; j += T) {
+      double* Rj = R + (size_t)j * n;
+      MGQP_UNROLL1
+      for (int i = qq; i < iq - 1; i++) Rj[i] = Rj[i + 1];
+      if (j < iq) Rj[iq - 1] = 0.0;
+    }
+    if (tid == 0) {
+      MGQP_UNROLL1
+      for (int i = qq; i < iq - 1; i++) {
+        A[i] = A[i + 1];
+        su[i] = su[i + 1];
+      }
+      A[iq - 1] = A[iq];
+      su[iq - 1] = su[iq];
+      A[iq] = 0;
+      su[iq] = 0.0;
+    }
+    iq--;
+    blk_sync();
+    if (iq == 0) return;
+    MGQP_UNROLL1
+    for (int j = qq; j < iq; j++) {
+      if (tid == 0) {
+        double cc = R[(size_t)j * n + j], ss = R[(size_t)(j + 1) * n + j];
+        const double h = ln_distance(cc, ss);
+        if (d_abs(h) < MGQP_EPS) {
+          sbc[3] = 0.0;
+        } else {
+          cc = d_div(cc, h);
+          ss = d_div(ss, h);
+          R[(size_t)(j + 1) * n + j] = 0.0;
+          if (cc < 0.0) {
+            R[(size_t)j * n + j] = -h;
+            cc = -cc;
+            ss = -ss;
+          } else {
+            R[(size_t)j * n + j] = h;
+          }
+          sbc[0] = cc;
+          sbc[1] = ss;
+          sbc[2] = d_div(ss, d_add(1.0, cc));
+          sbc[3] = 1.0;
+        }
+      }
+      blk_sync();
+      if (sbc[3] != 0.0) {
+        const double cc = sbc[0], ss = sbc[1], xny = sbc[2];
+        MGQP_UNROLL1
+        for (int k = j + 1 + tid; k < iq; k += T) {
+          const double t1 = R[(size_t)j * n + k], t2 = R[(size_t)(j + 1) * n + k];
+          const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
+          R[(size_t)j * n + k] = n1;
+          R[(size_t)(j + 1) * n + k] = d_sub(d_mul(xny, d_add(t1, n1)), t2);
+        }
+        MGQP_UNROLL1
+        for (int k = tid; k < n; k += T) {
+          double* Jk = J + (size_t)k * n;
+          const double t1 = Jk[j], t2 = Jk[j + 1];
+          const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
+          Jk[j] = n1;
+          Jk[j + 1] = d_sub(d_mul(xny, d_add(n1, t1)), t2);
+        }
+      }
+      blk_sync();
+    }
+  };
+
+  bool done = fail;
+
+  // ---------------------------------------------------------------- equality constraints
+  MGQP_UNROLL1
+  for (int e = 0; e < p && !done; e++) {
+    MGQP_UNROLL1
+    for (int j = tid; j < n; j += T) snp[j] = MGQP_LDG(io.CE + (size_t)j * p + e);
+    blk_sync();
+    direction();
+    dot0(sz, sz, 0);
+    dot0(snp, sx, 1);
+    dot0(sz, snp, 2);
+    blk_sync();
+    const double zz = sbc[0], npx = sbc[1], znp = sbc[2];
+    blk_sync();
+    double t2 = 0.0;
+    if (d_abs(zz) > MGQP_EPS) t2 = d_div(d_sub(-npx, MGQP_LDG(io.ce0 + e)), znp);
+    MGQP_UNROLL1
+    for (int k = tid; k < n; k += T) sx[k] = d_add(sx[k], d_mul(t2, sz[k]));
+    MGQP_UNROLL1
+    for (int k = tid; k < iq; k += T) su[k] = d_sub(su[k], d_mul(t2, sr[k]));
+    if (tid == 0) {
+      su[iq] = t2;
+      A[e] = -e - 1;
+    }
+    f = d_add(f, d_mul(d_mul(0.5, d_mul(t2, t2)), znp));
+    blk_sync();
+    if (!add_constraint()) {
+      status = 3;
+      done = true;
+    }
+  }
+
+  // ---------------------------------------------------------------- active-set iteration
+  MGQP_UNROLL1
+  for (int i = tid; i < m; i += T) act[i] = 0;
+  blk_sync();
+  const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
+  int ip = 0;
+  double ss = 0.0, s_ip = 0.0;
+  bool need_scan = true, l1 = true;
+
+  MGQP_UNROLL1
+  while (!done) {
+    if (need_scan) {
+      if (l1) {
+        MGQP_UNROLL1
+        for (int i = tid; i < m; i += T) excl[i] = 1;
+        ss = 0.0;
+        ip = 0;
+        blk_sync();
+      }
+      double best = ss, psi = 0.0;
+      int bidx = NONE;
+      MGQP_UNROLL1
+      for (int i0 = tid; i0 < m; i0 += 4 * T) {
+        // up to four columns per thread at a time: four independent accumulation chains
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int i1 = i0 + T, i2 = i0 + 2 * T, i3 = i0 + 3 * T;
+        const bool v1 = i1 < m, v2 = i2 < m, v3 = i3 < m;
+        MGQP_UNROLL1
+        for (int j = 0; j < n; j++) {
+          const double xj = sx[j];
+          const double* row = io.CI + (size_t)j * m;
+          a0 = mad<FMA>(MGQP_LDG(row + i0), xj, a0);
+          if (v1) a1 = mad<FMA>(MGQP_LDG(row + i1), xj, a1);
+          if (v2) a2 = mad<FMA>(MGQP_LDG(row + i2), xj, a2);
+          if (v3) a3 = mad<FMA>(MGQP_LDG(row + i3), xj, a3);
+        }
+        const double acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int i = i0 + c * T;
+          if (i < m) {
+            const double sum = d_add(acc[c], MGQP_LDG(io.ci0 + i));
+            sg[i] = sum;
+            if (sum < 0.0) psi = d_add(psi, sum);
+            if (sum < best && !act[i] && excl[i]) {
+              best = sum;
+              bidx = i;
+            }
+          }
+        }
+      }
+      double bval;
+      int bi;
+      block_argmin(best, bidx, bval, bi);
+      psi = block_sum(psi);
+      if (l1) {
+        if (!FMA && d_abs(psi) > d_mul(0.5, thr) && d_abs(psi) < d_mul(2.0, thr)) {
+          // within 2x of the threshold: redo the sum in the reference's order (rare)
+          if (tid == 0) {
+            double q = 0.0;
+            MGQP_UNROLL1
+            for (int i = 0; i < m; i++) q = d_add(q, (sg[i] < 0.0) ? sg[i] : 0.0);
+            sbc[0] = q;
+          }
+          blk_sync();
+          psi = sbc[0];
+          blk_sync();
+        }
+        if (d_abs(psi) <= thr) {
+          done = true;
+        } else {
+          MGQP_UNROLL1
+          for (int i = tid; i < iq; i += T) {
+            suold[i] = su[i];
+            Aold[i] = A[i];
+          }
+          MGQP_UNROLL1
+          for (int i = tid; i < n; i += T) sxold[i] = sx[i];
+        }
+      }
+      if (!done) {
+        if (bi != NONE) {
+          ss = bval;
+          ip = bi;
+          s_ip = bval;
+        }
+        if (ss >= 0.0) {
+          done = true;
+        } else {
+          MGQP_UNROLL1
+          for (int j = tid; j < n; j += T) snp[j] = MGQP_LDG(io.CI + (size_t)j * m + ip);
+          if (tid == 0) {
+            su[iq] = 0.0;
+            A[iq] = ip;
+          }
+          need_scan = false;
+        }
+      }
+      blk_sync();
+    }
+    if (done) break;
+
+    steps++;
+    if (steps > max_iter) {
+      status = 4;
+      break;
+    }
+    direction();
+
+    // step lengths
+    double ratio = INF;
+    int lk = NONE;
+    MGQP_UNROLL1
+    for (int k = p + tid; k < iq; k += T) {
+      if (sr[k] > 0.0) {
+        const double q = d_div(su[k], sr[k]);
+        if (q < ratio) {  // ascending k within a thread: first minimum wins
+          ratio = q;
+          lk = k;
+        }
+      }
+    }
+    double t1;
+    int lkk;
+    block_argmin(ratio, lk, t1, lkk);
+    const int l = (lkk == NONE) ? 0 : A[lkk];
+    dot0(sz, sz, 0);
+    dot0(sz, snp, 1);
+    blk_sync();
+    const double zz = sbc[0], znp = sbc[1];
+    const double uq = su[iq];
+    blk_sync();
+    double t2;
+    if (d_abs(zz) > MGQP_EPS) {
+      t2 = d_div(-s_ip, znp);
+      if (t2 < 0.0) t2 = INF;
+    } else {
+      t2 = INF;
+    }
+    const double t = (t2 < t1) ? t2 : t1;
+    if (t >= INF) {
+      status = 1;
+      f = INF;
+      break;
+    }
+    if (t2 >= INF) {
+      // dual step only
+      MGQP_UNROLL1
+      for (int k = tid; k < iq; k += T) su[k] = d_sub(su[k], d_mul(t, sr[k]));
+      if (tid == 0) {
+        su[iq] = d_add(uq, t);
+        act[l] = 0;
+      }
+      blk_sync();
+      delete_constraint(l);
+      continue;
+    }
+    MGQP_UNROLL1
+    for (int k = tid; k < n; k += T) sx[k] = d_add(sx[k], d_mul(t, sz[k]));
+    f = d_add(f, d_mul(d_mul(t, znp), d_add(d_mul(0.5, t), uq)));
+    MGQP_UNROLL1
+    for (int k = tid; k < iq; k += T) su[k] = d_sub(su[k], d_mul(t, sr[k]));
+    if (tid == 0) su[iq] = d_add(uq, t);
+    blk_sync();
+    if (d_abs(d_sub(t, t2)) < MGQP_EPS) {
+      if (!add_constraint()) {
+        if (tid == 0) excl[ip] = 0;
+        blk_sync();
+        delete_constraint(ip);
+        MGQP_UNROLL1
+        for (int i = tid; i < m; i += T) act[i] = 0;
+        blk_sync();
+        MGQP_UNROLL1
+        for (int i = p + tid; i < iq; i += T) {
+          A[i] = Aold[i];
+          su[i] = suold[i];
+          act[Aold[i]] = 1;
+        }
+        MGQP_UNROLL1
+        for (int i = tid; i < n; i += T) sx[i] = sxold[i];
+        need_scan = true;
+        l1 = false;
+      } else {
+        if (tid == 0) act[ip] = 1;
+        need_scan = true;
+        l1 = true;
+      }
+      blk_sync();
+      continue;
+    }
+    // partial step
+    if (tid == 0) act[l] = 0;
+    blk_sync();
+    delete_constraint(l);
+    dot0(snp, sx, 0);
+    blk_sync();
+    s_ip = d_add(sbc[0], MGQP_LDG(io.ci0 + ip));
+    blk_sync();
+  }
+
+  // ---------------------------------------------------------------- results
+  blk_sync();
+  MGQP_UNROLL1
+  for (int i = tid; i < n; i += T) out.x[i] = fail ? 0.0 : sx[i];
+  if (tid == 0) {
+    *out.f = f;
+    *out.status = status;
+    if (out.iq) *out.iq = iq;
+    if (out.iters) *out.iters = steps;
+  }
+  if (out.A) {
+    MGQP_UNROLL1
+    for (int i = tid; i < p + m; i += T) out.A[i] = (i < iq) ? A[i] : NONE;
+  }
+  blk_sync();
+}
+
+}  // namespace mgqp

@@ -1,0 +1,52 @@
+// Persistent CTA-per-QP kernel around gi_large_solve: each CTA pulls QP indices from the atomic
+// work queue and owns one slice of the global workspace (Cholesky factor | J | R | s).
+#pragma once
+#include "gi_large.cuh"
+
+namespace mgqp {
+
+struct LargeParams {
+  LargeView v;
+  long long batch;
+  const double* in[6];
+  long long stride[6];
+  double* x; double* f; int* status; int* iq; int* A; int* iters;
+  int max_iter;
+  unsigned* ticket;
+  double* workspace;  // gridDim.x * v.ws_doubles
+};
+
+template <bool FMA>
+__global__ void __launch_bounds__(512, 1) gi_large_kernel(const __grid_constant__ LargeParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long s_next;
+  double* ws = P.workspace + (size_t)blockIdx.x * P.v.ws_doubles;
+  long long q = -1;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      if (P.ticket) s_next = (long long)atomicAdd(P.ticket, 1u);
+      else s_next = (q < 0) ? (long long)blockIdx.x : q + gridDim.x;
+    }
+    __syncthreads();
+    q = s_next;
+    __syncthreads();
+    if (q >= P.batch) break;
+    LaneIO io;
+    io.G = P.in[0] + q * P.stride[0];
+    io.g0 = P.in[1] + q * P.stride[1];
+    io.CE = P.in[2] + q * P.stride[2];
+    io.ce0 = P.in[3] + q * P.stride[3];
+    io.CI = P.in[4] + q * P.stride[4];
+    io.ci0 = P.in[5] + q * P.stride[5];
+    LargeOut out;
+    out.x = P.x + q * P.v.n;
+    out.f = P.f + q;
+    out.status = P.status + q;
+    out.iq = P.iq ? P.iq + q : nullptr;
+    out.A = P.A ? P.A + q * (long long)(P.v.p + P.v.m) : nullptr;
+    out.iters = P.iters ? P.iters + q : nullptr;
+    gi_large_solve<FMA>(P.v, smem_raw, ws, io, P.max_iter, out);
+  }
+}
+
+}  // namespace mgqp

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "gi_lane_kernel.cuh"
+#include "gi_large_kernel.cuh"
 #include "gi_small_kernel.cuh"
 
 namespace {
@@ -58,6 +59,7 @@ struct DeviceCtx {
   bool attr_set[3][2] = {{false, false}, {false, false}, {false, false}};
   int attr_smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   int lane_attr_smem[9][2] = {};
+  int large_attr_smem[2] = {0, 0};
 };
 DeviceCtx g_dev[kMaxDev];
 
@@ -204,6 +206,56 @@ int launch_lane_n(DeviceCtx* ctx, const LanePlan& lp, const LaneParams& P, cudaS
   }
 }
 
+
+// ---------------------------------------------------------------- CTA-per-QP family (any n)
+struct LargePlan {
+  bool ok = false;
+  int T = 0;
+  LargeView v;
+};
+
+LargePlan make_large_plan(int n, int p, int m, int smem_optin) {
+  LargePlan lp;
+  int want = n > (m + 3) / 4 ? n : (m + 3) / 4;
+  int T = 64;
+  while (T < want && T < 512) T *= 2;
+  lp.T = T;
+  lp.v = make_large_view(n, p, m, T);
+  lp.ok = lp.v.smem_bytes + 1024 <= smem_optin && (long long)n * n < (1ll << 30);
+  return lp;
+}
+
+template <bool FMA>
+int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream_t st) {
+  auto kern = gi_large_kernel<FMA>;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->large_attr_smem[FMA] < lp.v.smem_bytes) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lp.v.smem_bytes));
+      ctx->large_attr_smem[FMA] = lp.v.smem_bytes;
+    }
+  }
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lp.T, lp.v.smem_bytes));
+  if (per_sm < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "CTA-per-QP kernel does not fit an SM (smem %d B)", lp.v.smem_bytes);
+  if (per_sm > 2) per_sm = 2;
+  long long ctas = (long long)ctx->sms * per_sm;
+  if (ctas > P.batch) ctas = P.batch;
+  const long long ws_bytes = lp.v.ws_doubles * 8;
+  const long long cap = (8ll << 30) / ws_bytes;  // keep the workspace under 8 GB
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "workspace of %lld bytes per QP is too large", ws_bytes);
+  void* ws = nullptr;
+  CU(cudaMallocAsync(&ws, (size_t)(ctas * ws_bytes), st));
+  P.workspace = static_cast<double*>(ws);
+  kern<<<(unsigned)ctas, lp.T, lp.v.smem_bytes, st>>>(P);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(ws, st);  // stream-ordered: released after the kernel has run
+  if (e != cudaSuccess) return fail(MGQP_ERR_CUDA, "gi_large_kernel launch failed: %s", cudaGetErrorString(e));
+  return MGQP_OK;
+}
+
 int validate(const mgqp_batch* d) {
   if (!d) return fail(MGQP_ERR_INVALID_ARG, "null batch descriptor");
   if (d->n < 1) return fail(MGQP_ERR_INVALID_ARG, "n = %d must be >= 1", d->n);
@@ -239,7 +291,7 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
     CU(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   }
   const bool fast = (d->flags & MGQP_FLAG_FAST_MATH) != 0;
-  if (!(d->flags & MGQP_FLAG_GROUP_KERNEL)) {
+  if (!(d->flags & (MGQP_FLAG_GROUP_KERNEL | MGQP_FLAG_CTA_KERNEL))) {
     const LanePlan lp = make_lane_plan(d->n, d->p, d->m, ctx->smem_optin);
     if (lp.ok) {
       LaneParams L;
@@ -263,10 +315,27 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
       return fast ? launch_lane_n<true>(ctx, lp, L, st) : launch_lane_n<false>(ctx, lp, L, st);
     }
   }
-  const Plan pl = make_plan(d->n, d->p, d->m, ctx->smem_optin);
-  if (pl.gw < 0)
-    return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "shape n=%d p=%d m=%d is outside the kernels built so far (n <= 32)", d->n,
-                d->p, d->m);
+  const Plan pl = (d->flags & MGQP_FLAG_CTA_KERNEL) ? Plan() : make_plan(d->n, d->p, d->m, ctx->smem_optin);
+  if (pl.gw < 0) {
+    const LargePlan lp = make_large_plan(d->n, d->p, d->m, ctx->smem_optin);
+    if (!lp.ok)
+      return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "shape n=%d p=%d m=%d needs %d B of shared memory per CTA", d->n, d->p,
+                  d->m, lp.v.smem_bytes);
+    LargeParams L;
+    memset(&L, 0, sizeof L);
+    L.v = lp.v;
+    L.batch = d->batch;
+    const double* lin[6] = {d->G, d->g0, d->CE, d->ce0, d->CI, d->ci0};
+    const long long lstride[6] = {d->sG, d->sg0, d->sCE, d->sce0, d->sCI, d->sci0};
+    for (int k = 0; k < 6; k++) {
+      L.in[k] = lin[k];
+      L.stride[k] = lstride[k];
+    }
+    L.x = d->x; L.f = d->f; L.status = d->status; L.iq = d->iq; L.A = d->A; L.iters = d->iters;
+    L.max_iter = max_iter;
+    L.ticket = ticket;
+    return fast ? launch_large<true>(ctx, lp, L, st) : launch_large<false>(ctx, lp, L, st);
+  }
 
   SmallParams P;
   memset(&P, 0, sizeof P);
@@ -532,6 +601,13 @@ int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int3
     return 1;
   }
   const Plan pl = make_plan(n, p, m, kSmemBudget);
+  if (pl.gw < 0) {
+    const LargePlan lg = make_large_plan(n, p, m, kSmemBudget);
+    if (!lg.ok) return -2;
+    if (smem_bytes_per_cta) *smem_bytes_per_cta = lg.v.smem_bytes;
+    if (warps_per_cta) *warps_per_cta = lg.T / 32;
+    return 0;
+  }
   if (smem_bytes_per_cta) *smem_bytes_per_cta = pl.smem;
   if (warps_per_cta) *warps_per_cta = pl.warps;
   return pl.gw;

@@ -120,3 +120,57 @@ extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const 
   }
   return 0;
 }
+
+// ------------------------------------------------------------------ CTA-per-QP solver (gi_large.cuh)
+#include "../../motion-generation-using-quadratic-programs_b200/csrc/gi_large.cuh"
+
+namespace {
+struct LargeJob {
+  LargeView v;
+  unsigned char* smem;
+  double* ws;
+  LaneIO io;
+  int max_iter, fma;
+  LargeOut out;
+};
+void large_body(void* a) {
+  LargeJob* j = (LargeJob*)a;
+  if (j->fma) gi_large_solve<true>(j->v, j->smem, j->ws, j->io, j->max_iter, j->out);
+  else gi_large_solve<false>(j->v, j->smem, j->ws, j->io, j->max_iter, j->out);
+}
+}  // namespace
+
+extern "C" int emu_large_solve_batch(int n, int p, int m, long long batch, const double* G, const double* g0,
+                                     const double* CE, const double* ce0, const double* CI, const double* ci0,
+                                     double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
+                                     int nthreads, int fma, int threads) {
+  if (nthreads > MGQP_EMU_MAX || (nthreads & (nthreads - 1))) return -2;
+  const LargeView v = make_large_view(n, p, m, nthreads);
+  if (max_iter <= 0) max_iter = 100 + 10 * (p + m);
+  std::atomic<long long> next(0);
+  auto work = [&]() {
+    std::vector<unsigned char> smem(v.smem_bytes + 16);
+    std::vector<double> ws(v.ws_doubles);
+    for (;;) {
+      const long long b = next.fetch_add(1);
+      if (b >= batch) break;
+      LargeJob j;
+      j.v = v;
+      j.smem = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+      j.ws = ws.data();
+      j.io = LaneIO{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI + b * (long long)n * m, ci0 + b * m};
+      j.max_iter = max_iter;
+      j.fma = fma;
+      j.out.x = x + b * n; j.out.f = f + b; j.out.status = status + b;
+      j.out.iq = iq ? iq + b : nullptr;
+      j.out.A = A ? A + b * (p + m) : nullptr;
+      j.out.iters = iters ? iters + b : nullptr;
+      emu_run_block(large_body, &j, nthreads);
+    }
+  };
+  if (threads <= 1) { work(); return 0; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  return 0;
+}

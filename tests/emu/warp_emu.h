@@ -29,15 +29,17 @@
 
 namespace mgqp {
 
+#define MGQP_EMU_MAX 128
 struct EmuWarp {
   ucontext_t sched;
-  ucontext_t ctx[32];
-  char* stack[32];
-  bool finished[32];
-  uint64_t slot[2][32];
-  uint32_t kind[2][32];
-  uint32_t seq[32];
+  ucontext_t ctx[MGQP_EMU_MAX];
+  char* stack[MGQP_EMU_MAX];
+  bool finished[MGQP_EMU_MAX];
+  uint64_t slot[2][MGQP_EMU_MAX];
+  uint32_t kind[2][MGQP_EMU_MAX];
+  uint32_t seq[MGQP_EMU_MAX];
   int cur;
+  int nthreads;
   void (*body)(void*);
   void* arg;
   long rendezvous;
@@ -53,18 +55,20 @@ static void emu_trampoline() {
 }
 
 // run body(arg) on 32 lock-step lanes
-static inline void emu_run_warp(void (*body)(void*), void* arg) {
+static inline void emu_run_block(void (*body)(void*), void* arg, int nthreads) {
   static thread_local EmuWarp* w = nullptr;
   const size_t STK = 256 * 1024;
   if (!w) {
     w = (EmuWarp*)calloc(1, sizeof(EmuWarp));
-    for (int i = 0; i < 32; i++) w->stack[i] = (char*)malloc(STK);
+    for (int i = 0; i < MGQP_EMU_MAX; i++) w->stack[i] = (char*)malloc(STK);
   }
   g_emu = w;
   w->body = body;
   w->arg = arg;
   w->rendezvous = 0;
-  for (int i = 0; i < 32; i++) {
+  w->nthreads = nthreads;
+  const int NT = nthreads;
+  for (int i = 0; i < NT; i++) {
     w->finished[i] = false;
     w->seq[i] = 0;
     getcontext(&w->ctx[i]);
@@ -75,7 +79,7 @@ static inline void emu_run_warp(void (*body)(void*), void* arg) {
   }
   for (;;) {
     int alive = 0;
-    for (int i = 0; i < 32; i++) {
+    for (int i = 0; i < NT; i++) {
       if (w->finished[i]) continue;
       alive++;
       w->cur = i;
@@ -84,7 +88,7 @@ static inline void emu_run_warp(void (*body)(void*), void* arg) {
     if (!alive) break;
     // after a full round every unfinished lane sits at a rendezvous: check they agree
     int first = -1;
-    for (int i = 0; i < 32; i++) {
+    for (int i = 0; i < NT; i++) {
       if (w->finished[i]) continue;
       if (first < 0) first = i;
       const int par = (w->seq[i] - 1) & 1;
@@ -96,14 +100,16 @@ static inline void emu_run_warp(void (*body)(void*), void* arg) {
       }
     }
     int fin = 0;
-    for (int i = 0; i < 32; i++) fin += w->finished[i];
-    if (fin != 0 && fin != 32) {
+    for (int i = 0; i < NT; i++) fin += w->finished[i];
+    if (fin != 0 && fin != NT) {
       fprintf(stderr, "EMU: %d lanes exited while others wait at a warp primitive\n", fin);
       abort();
     }
     w->rendezvous++;
   }
 }
+
+static inline void emu_run_warp(void (*body)(void*), void* arg) { emu_run_block(body, arg, 32); }
 
 // publish + yield; returns the parity buffer holding this round's operands
 static inline int emu_meet(uint32_t kind, uint64_t v) {
@@ -122,6 +128,10 @@ static inline uint64_t emu_bits(double v) { uint64_t b; memcpy(&b, &v, 8); retur
 static inline double emu_dbl(uint64_t b) { double v; memcpy(&v, &b, 8); return v; }
 
 MGQP_DEV int wp_lane() { return g_emu->cur; }
+// thread-block view of the same fibers (gi_large.cuh)
+MGQP_DEV int blk_tid() { return g_emu->cur; }
+MGQP_DEV int blk_dim() { return g_emu->nthreads; }
+MGQP_DEV void blk_sync() { emu_meet(20, 0); }
 MGQP_DEV void wp_sync() { emu_meet(1, 0); }
 MGQP_DEV bool wp_any(bool p) {
   const int par = emu_meet(2, p);

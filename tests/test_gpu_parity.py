@@ -54,8 +54,6 @@ def test_golden_fixtures_from_reference_binary(gpu, path):
     """x / f / verdict the reference's shipped binary produced (tests/golden/make_golden.py)."""
     z = np.load(path)
     n = z["g0"].shape[1]
-    if n > 32:
-        pytest.skip("n > 32 is served by the CTA-per-QP kernel (not built yet)")
     b = workloads.QPBatch("golden", n, z["ce0"].shape[1], z["ci0"].shape[1], z["G"], z["g0"], z["CE"], z["ce0"], z["CI"], z["ci0"])
     got = _solve(gpu, b)
     assert_bit_identical(dict(x=got["x"], f=got["f"], status=got["status"]), dict(x=z["x"], f=z["f"], status=z["status"]),
@@ -80,6 +78,43 @@ def test_staging_schedule_and_kernel_family_variants(gpu, restatement, flags):
     one-QP-per-lane kernel) must not change a bit."""
     b = workloads.make("C2", 5003)
     assert_bit_identical(_solve(gpu, b, flags=flags), _oracle(restatement, b), f"flags{flags}")
+
+
+@pytest.mark.parametrize("n,p,m", [(33, 0, 70), (40, 3, 90), (50, 5, 160), (64, 8, 100), (100, 0, 300), (7, 1, 42),
+                                   (14, 10, 28), (6, 0, 200)])
+def test_cta_per_qp_kernel_bit_identical(gpu, restatement, n, p, m):
+    """The CTA-per-QP family (n > 32; forced with flag 16 on the small shapes)."""
+    b = workloads.make_random(96, n, p, m, seed=7 * n + m, box=(m >= 2 * n))
+    assert_bit_identical(_solve(gpu, b, flags=16), _oracle(restatement, b), f"cta R{n}_{p}_{m}")
+
+
+def test_cta_per_qp_kernel_failures_and_degenerate(gpu, restatement):
+    from test_emu_lockstep import _degenerate_batch
+    b = _degenerate_batch(256)
+    for cap in (7, 60):
+        assert_bit_identical(_solve(gpu, b, max_iter=cap, flags=16), _oracle(restatement, b, max_iter=cap), f"cta cap{cap}")
+    b = workloads.make_random(256, 6, 2, 14, seed=11, box=True)
+    b.CE[0::4, :, 1] = -0.5 * b.CE[0::4, :, 0]
+    b.G[1::8] -= 4.0 * np.eye(6)
+    b.ci0[2::8, 0] = -3.0; b.ci0[2::8, 6] = 1.0
+    ref = _oracle(restatement, b)
+    got = _solve(gpu, b, flags=16)
+    assert np.array_equal(got["status"], ref["status"])
+    keep = ref["status"] != 2
+    for k in ("x", "iq", "iters", "A"):
+        assert np.array_equal(got[k][keep], ref[k][keep]), k
+    assert np.array_equal(got["f"], ref["f"], equal_nan=True)
+
+
+def test_mpc_shape_against_reference_binary_and_oracle(gpu, restatement):
+    """BASELINE config 4 shape: n = 350, m = 2100.  One QP is pinned by the shipped binary
+    (tests/golden/batch_C4_seedonly.npz); a small batch is checked against the oracle."""
+    z = np.load(os.path.join(GOLDEN, "batch_C4_seedonly.npz"))
+    b = workloads.make("C4", 1)
+    got = _solve(gpu, b)
+    assert np.array_equal(got["x"], z["x"]) and np.array_equal(got["f"], z["f"]) and np.array_equal(got["status"], z["status"])
+    b = workloads.make("C4", 6, seed=99)
+    assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), "C4")
 
 
 def test_tail_and_tiny_batches(gpu, restatement):
