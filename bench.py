@@ -35,8 +35,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-QPS_PER_GPU = {"C2": 1_000_000, "C5": 1_000_000, "C3": 100_000, "S0": 400_000, "S2": 400_000}
-CPU_SAMPLE = {"C2": 200_000, "C5": 200_000, "C3": 60_000, "S0": 60_000, "S2": 100_000}
+QPS_PER_GPU = {"C2": 1_000_000, "C5": 1_000_000, "C3": 100_000, "C4": 592, "S0": 400_000, "S2": 400_000}
+CPU_SAMPLE = {"C2": 200_000, "C5": 200_000, "C3": 60_000, "C4": 16, "S0": 60_000, "S2": 100_000}
 
 
 def host_threads() -> int:
@@ -256,6 +256,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     kern_ms = float(np.mean(step_ms))  # one launch per step: the step IS the kernel (+ a 4-byte memset)
     achieved = B * bytes_per_qp / (kern_ms / 1e3) / 1e9
     gw, warps, smem = mgqp_b200.plan(n, p, m)
+    kname = {1: "gi_lane_kernel<%d> (one QP per lane)" % n, 0: "gi_large_kernel (one QP per CTA)"}.get(
+        gw, "gi_small_kernel<%d> (%d lanes per QP)" % (gw, gw))
+    if args.flags & 8:
+        kname = "gi_small_kernel (lane groups, forced)"
+    if args.flags & 16:
+        kname = "gi_large_kernel (one QP per CTA, forced)"
     line = {
         "metric": "batched QP solves/sec (fp64)", "value": value, "unit": "QP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -263,7 +269,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": f"{name}: {B} QPs per GPU, n={n} p={p} m={m} (BASELINE.json configs[1] shape)",
                    "l2": f"inputs {B * bytes_per_qp / 1e6:.0f} MB per step > 126 MB L2, read once per step",
                    "mode": "fast_math" if args.flags & 1 else "exact (bit-identical to QuadProg++)",
-                   "kernel": f"gi_small_kernel<{gw}> {warps} warps/CTA {smem} B smem", "flags": args.flags,
+                   "kernel": f"{kname}, {warps} warps/CTA, {smem} B smem/CTA", "flags": args.flags,
                    "status_counts": np.bincount(status, minlength=5).tolist()},
         "gpu_launches": int(launches),
         "clocks": clocks,

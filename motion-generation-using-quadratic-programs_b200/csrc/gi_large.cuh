@@ -23,12 +23,22 @@
 #pragma once
 #include "gi_lane.cuh"  // LaneIO, ln_distance, MGQP_LDG, MGQP_EPS
 
+#ifdef MGQP_EMULATE
+#define MGQP_UNROLL8
+#define MGQP_UNROLL4
+#else
+#define MGQP_UNROLL8 _Pragma("unroll 8")
+#define MGQP_UNROLL4 _Pragma("unroll 4")
+#endif
+
 namespace mgqp {
+
+#define MGQP_ROWBLK 8
 
 struct LargeView {
   int n, p, m, T;
   // shared memory, in doubles from the (16-byte aligned) base
-  int ox, oz, od, onp, orr, ou, oxold, ouold, oh, occ, oss, oxny, ored, obc;
+  int ox, oz, od, onp, orr, ou, oxold, ouold, oh, occ, oss, oxny, ored, obc, orow;
   int oredi, oA, oAold;   // ints, byte offsets
   int oact, oexcl, oskip; // bytes, byte offsets
   int smem_bytes;
@@ -53,6 +63,7 @@ MGQP_HOST inline LargeView make_large_view(int n, int p, int m, int T) {
   v.oxny = o; o += n + 1;
   v.ored = o; o += T;
   v.obc = o; o += 16;
+  v.orow = o; o += 2 * MGQP_ROWBLK * n;  // double-buffered block of R / L rows for the serial solves
   int b = o * 8;
   v.oredi = b; b += 4 * T;
   v.oA = b; b += 4 * (n + 2);
@@ -89,6 +100,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   double* sxny = sm + v.oxny;
   double* sred = sm + v.ored;
   double* sbc = sm + v.obc;    // broadcast slots
+  double* srow = sm + v.orow;  // 2 x MGQP_ROWBLK rows
   int* sredi = reinterpret_cast<int*>(smem + v.oredi);
   int* A = reinterpret_cast<int*>(smem + v.oA);
   int* Aold = reinterpret_cast<int*>(smem + v.oAold);
@@ -145,6 +157,55 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     }
   };
 
+  // out[i] = (rhs[i] - sum_{j=i+1}^{k-1} U[i][j]*out[j]) / U[i][i] for i = k-1 .. 0, the sum in
+  // ascending j (update_r / backward_elimination).  The recurrence is serial by construction (row i
+  // needs out[i+1] before its first addition), so one thread runs it -- but from shared memory:
+  // the other threads stream the rows in, MGQP_ROWBLK at a time, one block ahead of the consumer.
+  // running == true: backward_elimination's form, a = rhs[i]; a -= U[i][j]*out[j]; out[i] = a / U[i][i].
+  auto upper_solve = [&](const double* U, int k, const double* rhs, double* outv, bool running) {
+    const int nb = (k + MGQP_ROWBLK - 1) / MGQP_ROWBLK;
+    auto fetch = [&](int b, int first, int step) {
+      const int hi = k - b * MGQP_ROWBLK;
+      const int lo = hi - MGQP_ROWBLK > 0 ? hi - MGQP_ROWBLK : 0;
+      double* buf = srow + (size_t)(b & 1) * MGQP_ROWBLK * n;
+      MGQP_UNROLL1
+      for (int r = lo; r < hi; r++) {
+        const double* Ur = U + (size_t)r * n;
+        double* br = buf + (size_t)(r - lo) * n;
+        MGQP_UNROLL4
+        for (int j = r + first; j < k; j += step) br[j] = Ur[j];
+      }
+    };
+    if (nb > 0) fetch(0, tid, T);
+    blk_sync();
+    MGQP_UNROLL1
+    for (int b = 0; b < nb; b++) {
+      if (tid == 0) {
+        const int hi = k - b * MGQP_ROWBLK;
+        const int lo = hi - MGQP_ROWBLK > 0 ? hi - MGQP_ROWBLK : 0;
+        const double* buf = srow + (size_t)(b & 1) * MGQP_ROWBLK * n;
+        MGQP_UNROLL1
+        for (int i = hi - 1; i >= lo; i--) {
+          const double* Ui = buf + (size_t)(i - lo) * n;
+          if (running) {
+            double a = rhs[i];
+            MGQP_UNROLL4
+            for (int j = i + 1; j < k; j++) a = msub<FMA>(a, Ui[j], outv[j]);
+            outv[i] = d_div(a, Ui[i]);
+          } else {
+            double s = 0.0;
+            MGQP_UNROLL4
+            for (int j = i + 1; j < k; j++) s = mad<FMA>(Ui[j], outv[j], s);
+            outv[i] = d_div(d_sub(rhs[i], s), Ui[i]);
+          }
+        }
+      } else if (b + 1 < nb) {
+        fetch(b + 1, tid - 1, T - 1);
+      }
+      blk_sync();
+    }
+  };
+
   int status = 0, iq = 0, steps = 0;
   double f = 0.0;
 
@@ -175,7 +236,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int j = i + tid; j < n; j += T) {
       double sum = Gc[(size_t)i * n + j];
       const double* rowj = Gc + (size_t)j * n;
-      MGQP_UNROLL1
+      MGQP_UNROLL8
       for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sz[k], rowj[k]);
       sd[j] = sum;
     }
@@ -211,7 +272,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
       for (int r = 0; r < n; r++) {
         double acc = (r == i) ? 1.0 : 0.0;
         const double* Lr = Gc + (size_t)r * n;
-        MGQP_UNROLL1
+        MGQP_UNROLL8
         for (int j = 0; j < r; j++) acc = msub<FMA>(acc, Lr[j], Ji[j]);
         Ji[r] = d_div(acc, Lr[r]);
       }
@@ -230,16 +291,9 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
       for (int i = j + 1 + tid; i < n; i += T) sd[i] = msub<FMA>(sd[i], Gc[(size_t)i * n + j], yj);
       blk_sync();
     }
-    // backward elimination, c2, f: serial (ascending-j subtraction is the reverse of availability)
+    // backward elimination (serial: its ascending-j subtraction is the reverse of availability), c2, f
+    upper_solve(Gc, n, sz, sx, true);
     if (tid == 0) {
-      MGQP_UNROLL1
-      for (int i = n - 1; i >= 0; i--) {
-        double a = sz[i];
-        const double* Ui = Gc + (size_t)i * n;
-        MGQP_UNROLL1
-        for (int j = i + 1; j < n; j++) a = msub<FMA>(a, Ui[j], sx[j]);
-        sx[i] = d_div(a, Ui[i]);
-      }
       double t = 0.0, fs = 0.0;
       MGQP_UNROLL1
       for (int i = 0; i < n; i++) {
@@ -261,7 +315,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     MGQP_UNROLL1
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
-      MGQP_UNROLL1
+      MGQP_UNROLL8
       for (int j = 0; j < n; j++) s = mad<FMA>(J[(size_t)j * n + i], snp[j], s);
       sd[i] = s;
     }
@@ -270,21 +324,12 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
       const double* Ji = J + (size_t)i * n;
-      MGQP_UNROLL1
+      MGQP_UNROLL8
       for (int j = iq; j < n; j++) s = mad<FMA>(Ji[j], sd[j], s);
       sz[i] = s;
     }
-    if (tid == 0) {
-      MGQP_UNROLL1
-      for (int i = iq - 1; i >= 0; i--) {
-        double s = 0.0;
-        const double* Ri = R + (size_t)i * n;
-        MGQP_UNROLL1
-        for (int j = i + 1; j < iq; j++) s = mad<FMA>(Ri[j], sr[j], s);
-        sr[i] = d_div(d_sub(sd[i], s), Ri[i]);
-      }
-    }
     blk_sync();
+    upper_solve(R, iq, sd, sr, false);
   };
 
   // add_constraint (Appendix A).  Returns the reference's bool; iq is incremented.
@@ -342,7 +387,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int k = tid; k < n; k += T) {
       double* Jk = J + (size_t)k * n;
       double t2 = Jk[n - 1];
-      MGQP_UNROLL1
+      MGQP_UNROLL8
       for (int j = n - 1; j >= iq + 1; j--) {
         const double t1 = Jk[j - 1];
         if (!skip[j]) {
@@ -511,7 +556,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const int i1 = i0 + T, i2 = i0 + 2 * T, i3 = i0 + 3 * T;
         const bool v1 = i1 < m, v2 = i2 < m, v3 = i3 < m;
-        MGQP_UNROLL1
+        MGQP_UNROLL4
         for (int j = 0; j < n; j++) {
           const double xj = sx[j];
           const double* row = io.CI + (size_t)j * m;
