@@ -39,6 +39,16 @@ QPS_PER_GPU = {"C2": 1_000_000, "C5": 1_000_000, "C3": 100_000, "C4": 592, "S0":
 CPU_SAMPLE = {"C2": 200_000, "C5": 200_000, "C3": 60_000, "C4": 16, "S0": 60_000, "S2": 100_000}
 
 
+CONFIG_NOTE = {
+    "C2": "BASELINE.json configs[1]: 1M independent random 7-DoF mgqp QPs",
+    "C5": "BASELINE.json configs[4] shape: scenario sweep, ~10 % infeasible",
+    "C3": "BASELINE.json configs[2]: task-space QPs with slacks",
+    "C4": "BASELINE.json configs[3]: horizon-stacked MPC QPs, 7 DoF x 50 steps",
+    "S0": "as-shipped mgqp level 0 (src/mgqp.cpp:1076-1143)",
+    "S2": "as-shipped mgqp level 2",
+}
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -266,7 +276,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "metric": "batched QP solves/sec (fp64)", "value": value, "unit": "QP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: {B} QPs per GPU, n={n} p={p} m={m} (BASELINE.json configs[1] shape)",
+        "config": {"workload": f"{name}: {B} QPs per GPU, n={n} p={p} m={m} ({CONFIG_NOTE[name]})",
                    "l2": f"inputs {B * bytes_per_qp / 1e6:.0f} MB per step > 126 MB L2, read once per step",
                    "mode": "fast_math" if args.flags & 1 else "exact (bit-identical to QuadProg++)",
                    "kernel": f"{kname}, {warps} warps/CTA, {smem} B smem/CTA", "flags": args.flags,
@@ -299,7 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(QPS_PER_GPU))
+    ap.add_argument("--workload", default="C2", choices=sorted(QPS_PER_GPU))  # C2 = the headline config
     ap.add_argument("--batch", type=int, default=0, help="QPs per GPU per step (default: the workload's)")
     ap.add_argument("--flags", type=int, default=0, help="MGQP_FLAG_* bits (1 = fast math)")
     ap.add_argument("--e2e-steps", type=int, default=3)

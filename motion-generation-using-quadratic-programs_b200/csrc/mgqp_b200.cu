@@ -60,6 +60,11 @@ struct DeviceCtx {
   int attr_smem[3][2] = {{0, 0}, {0, 0}, {0, 0}};
   int lane_attr_smem[9][2] = {};
   int large_attr_smem[2] = {0, 0};
+  // host-buffer pipeline: two streams and two staging arenas, kept across calls (grow only)
+  std::mutex host_mu;
+  cudaStream_t host_st[2] = {nullptr, nullptr};
+  void* arena[2] = {nullptr, nullptr};
+  size_t arena_cap[2] = {0, 0};
 };
 DeviceCtx g_dev[kMaxDev];
 
@@ -381,36 +386,30 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
 struct DevBufs {
   double *G = nullptr, *g0 = nullptr, *CE = nullptr, *ce0 = nullptr, *CI = nullptr, *ci0 = nullptr, *x = nullptr, *f = nullptr;
   int *status = nullptr, *iq = nullptr, *A = nullptr, *iters = nullptr;
-  void* all[12] = {};
-  int free_all() {
-    for (void* p : all)
-      if (p) cudaFree(p);
-    return 0;
-  }
 };
 
-int alloc_bufs(DevBufs& b, const mgqp_batch* h, long long chunk) {
+// Carve the staging buffers of one chunk out of one arena (256-byte aligned pieces).
+size_t carve_bufs(DevBufs& b, const mgqp_batch* h, long long chunk, char* base) {
   const long long n = h->n, p = h->p, m = h->m;
-  auto al = [&](void** dst, long long bytes, int slot) -> int {
-    if (bytes <= 0) bytes = 16;
-    CU(cudaMalloc(dst, (size_t)bytes));
-    b.all[slot] = *dst;
-    return MGQP_OK;
+  size_t off = 0;
+  auto take = [&](long long bytes) -> char* {
+    char* ptr = base ? base + off : nullptr;
+    off += (size_t)((bytes > 0 ? bytes : 16) + 255) & ~(size_t)255;
+    return ptr;
   };
-  int rc;
-  if ((rc = al((void**)&b.G, chunk * n * n * 8, 0))) return rc;
-  if ((rc = al((void**)&b.g0, chunk * n * 8, 1))) return rc;
-  if ((rc = al((void**)&b.CE, chunk * n * p * 8, 2))) return rc;
-  if ((rc = al((void**)&b.ce0, chunk * p * 8, 3))) return rc;
-  if ((rc = al((void**)&b.CI, chunk * n * m * 8, 4))) return rc;
-  if ((rc = al((void**)&b.ci0, chunk * m * 8, 5))) return rc;
-  if ((rc = al((void**)&b.x, chunk * n * 8, 6))) return rc;
-  if ((rc = al((void**)&b.f, chunk * 8, 7))) return rc;
-  if ((rc = al((void**)&b.status, chunk * 4, 8))) return rc;
-  if (h->iq && (rc = al((void**)&b.iq, chunk * 4, 9))) return rc;
-  if (h->A && (rc = al((void**)&b.A, chunk * (p + m) * 4, 10))) return rc;
-  if (h->iters && (rc = al((void**)&b.iters, chunk * 4, 11))) return rc;
-  return MGQP_OK;
+  b.G = (double*)take(chunk * n * n * 8);
+  b.g0 = (double*)take(chunk * n * 8);
+  b.CE = (double*)take(chunk * n * p * 8);
+  b.ce0 = (double*)take(chunk * p * 8);
+  b.CI = (double*)take(chunk * n * m * 8);
+  b.ci0 = (double*)take(chunk * m * 8);
+  b.x = (double*)take(chunk * n * 8);
+  b.f = (double*)take(chunk * 8);
+  b.status = (int*)take(chunk * 4);
+  b.iq = (int*)take(chunk * 4);
+  b.A = (int*)take(chunk * (p + m) * 4);
+  b.iters = (int*)take(chunk * 4);
+  return off;
 }
 
 // Upload / solve / download QPs [q0, q0+cnt) of host batch h through buffers b on stream st.
@@ -469,12 +468,21 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
   CU(cudaSetDevice(device));
   if (chunk > h->batch) chunk = h->batch;
   if (chunk < 1) return MGQP_OK;
-  cudaStream_t st[2];
-  DevBufs bufs[2];
+  std::lock_guard<std::mutex> host_lock(ctx->host_mu);  // one host-buffer call per device at a time
+  DevBufs probe, bufs[2];
+  const size_t need = carve_bufs(probe, h, chunk, nullptr);
   for (int i = 0; i < 2; i++) {
-    CU(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    if ((rc = alloc_bufs(bufs[i], h, chunk))) break;
+    if (!ctx->host_st[i]) CU(cudaStreamCreateWithFlags(&ctx->host_st[i], cudaStreamNonBlocking));
+    if (ctx->arena_cap[i] < need) {
+      if (ctx->arena[i]) CU(cudaFree(ctx->arena[i]));
+      ctx->arena[i] = nullptr;
+      ctx->arena_cap[i] = 0;
+      CU(cudaMalloc(&ctx->arena[i], need));
+      ctx->arena_cap[i] = need;
+    }
+    carve_bufs(bufs[i], h, chunk, static_cast<char*>(ctx->arena[i]));
   }
+  cudaStream_t* st = ctx->host_st;
   int k = 0;
   while (!rc) {
     const long long q0 = next->fetch_add(chunk);
@@ -488,8 +496,6 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
   for (int i = 0; i < 2; i++) {
     cudaError_t e = cudaStreamSynchronize(st[i]);
     if (e != cudaSuccess && !rc) rc = fail(MGQP_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
-    cudaStreamDestroy(st[i]);
-    bufs[i].free_all();
   }
   return rc;
 }
