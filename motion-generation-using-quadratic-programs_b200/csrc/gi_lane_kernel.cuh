@@ -4,8 +4,9 @@
 // There is no staging pass: every lane reads its own QP's G, g0, CI and ci0 straight from global
 // memory inside gi_lane_solve (consecutive 8-byte loads of one lane share 32-byte sectors, so HBM
 // sees every byte once and L1 serves the rest); only x goes through shared memory on the way out
-// so that its stores are coalesced.  The next tile is prefetched into L2 with
-// cp.async.bulk.prefetch while the current one is solved.
+// so that its stores are coalesced.  (An L2 prefetch of the next tile was measured and removed: it
+// doubled the DRAM read traffic -- the lines were evicted before use -- without changing the run
+// time; profiles/r01_notes.md.)
 #pragma once
 #include "gi_lane.cuh"
 
@@ -19,22 +20,7 @@ struct LaneParams {
   double* x; double* f; int* status; int* iq; int* A; int* iters;
   int max_iter;
   unsigned* ticket;
-  unsigned prefetch_mask;  // fields whose next-tile block is contiguous and 16-byte aligned
 };
-
-__device__ __forceinline__ void lane_prefetch_l2(const void* src, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int K>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(K) : "memory");
-}
 
 template <int N, bool FMA>
 __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__ LaneParams P) {
@@ -47,7 +33,6 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
   double* S = ws + lane * stride;
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   const long long my_warp = (long long)blockIdx.x * warps_per_cta + warp;
-  const int sizes[6] = {n * n, n, n * p, p, n * m, m};
 
   auto next_tile = [&](long long prev) -> long long {
     if (P.ticket) {
@@ -64,18 +49,6 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
     const long long rem = P.batch - q0;
     const int cnt = rem < 32 ? (int)rem : 32;
     const long long tile_next = next_tile(tile);
-    if (tile_next < P.tiles && (tile_next + 1) * 32 <= P.batch && lane < 6 && (P.prefetch_mask & (1u << lane))) {
-      // one contiguous block per field: 32 QPs x size doubles (<= 75 KB for CI at n=7, m=42)
-      const char* src = reinterpret_cast<const char*>(P.in[lane] + tile_next * 32 * P.stride[lane]);
-      unsigned bytes = 32u * (unsigned)sizes[lane] * 8u;
-      while (bytes) {  // the prefetch size field is limited; go in 16 KB pieces
-        const unsigned b = bytes > 16384u ? 16384u : bytes;
-        lane_prefetch_l2(src, b);
-        src += b;
-        bytes -= b;
-      }
-    }
-
     const long long myq = q0 + (lane < cnt ? lane : 0);
     LaneIO io;
     io.G = P.in[0] + myq * P.stride[0];

@@ -306,13 +306,9 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
       L.tiles = (d->batch + 31) / 32;
       const double* in[6] = {d->G, d->g0, d->CE, d->ce0, d->CI, d->ci0};
       const long long stride[6] = {d->sG, d->sg0, d->sCE, d->sce0, d->sCI, d->sci0};
-      const int size[6] = {d->n * d->n, d->n, d->n * d->p, d->p, d->n * d->m, d->m};
       for (int k = 0; k < 6; k++) {
         L.in[k] = in[k];
         L.stride[k] = stride[k];
-        if (size[k] > 0 && stride[k] == size[k] && (32ll * size[k] * 8) % 16 == 0 &&
-            (reinterpret_cast<uintptr_t>(in[k]) % 16) == 0 && !(d->flags & MGQP_FLAG_NO_BULK_COPY))
-          L.prefetch_mask |= 1u << k;
       }
       L.x = d->x; L.f = d->f; L.status = d->status; L.iq = d->iq; L.A = d->A; L.iters = d->iters;
       L.max_iter = max_iter;
