@@ -180,7 +180,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dev = torch.device(f"cuda:{local_rank}")
     name = args.workload
     B = args.batch or QPS_PER_GPU[name]
-    b = workloads.make(name, B, seed=1234 + 2 + 1000 * rank if rank else None)
+    from mgqp_b200 import sharding
+    b = workloads.make(name, B, seed=sharding.rank_seed(1234 + workloads._CONFIG_ID[name], rank) if rank else None)
     n, p, m = b.n, b.p, b.m
     bytes_per_qp = mgqp_b200.algorithmic_bytes(n, p, m)
 
