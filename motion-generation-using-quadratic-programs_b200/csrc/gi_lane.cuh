@@ -124,9 +124,19 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 
   int status = 0, iq = 0, steps = 0;
   double f = 0.0;
+  bool has_dense = false;  // some inequality column has more than one nonzero
   double x[N], z[N], np[N], dd[N], xold[N];
 #pragma unroll
   for (int i = 0; i < N; i++) { x[i] = 0.0; z[i] = 0.0; np[i] = 0.0; dd[i] = 0.0; xold[i] = 0.0; }
+
+  // G and g0 first: their loads are in flight while the constraint columns are being classified
+  double L[N][N], g0r[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int j = 0; j < N; j++) L[i][j] = MGQP_LDG(io.G + i * N + j);
+    g0r[i] = MGQP_LDG(io.g0 + i);
+  }
 
   // ---------------------------------------------------------------- inequality columns: classify
   // Row-major sweep of this QP's CI straight from global memory (each 32-byte sector is fetched from
@@ -144,6 +154,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           civ[i] = a;
         } else {
           cidx[i] = LN_DENSE;
+          has_dense = true;
         }
       }
     };
@@ -152,7 +163,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       // 16-byte loads, 8 in flight: a 32-byte sector is consumed by two back-to-back loads of the
       // same lane instead of living in L1 across loop iterations
       int j = 0, i = 0;
-#pragma unroll 8
+#pragma unroll 12
       for (int e = 0; e < nm; e += 2) {
         double a0, a1;
         MGQP_LDG2(io.CI + e, a0, a1);
@@ -169,18 +180,21 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
         for (int i = 0; i < m; i++) classify(MGQP_LDG(row + i), j, i);
       }
     }
+    if (((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.ci0) & 15ull) == 0ull)) {
+#pragma unroll 11
+      for (int i = 0; i < m; i += 2) {
+        double a0, a1;
+        MGQP_LDG2(io.ci0 + i, a0, a1);
+        sci0[i] = a0;
+        sci0[i + 1] = a1;
+      }
+    } else {
 #pragma unroll 6
-    for (int i = 0; i < m; i++) sci0[i] = MGQP_LDG(io.ci0 + i);
+      for (int i = 0; i < m; i++) sci0[i] = MGQP_LDG(io.ci0 + i);
+    }
   }
 
   // ---------------------------------------------------------------- set-up in registers
-  double L[N][N], g0r[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-#pragma unroll
-    for (int j = 0; j < N; j++) L[i][j] = MGQP_LDG(io.G + i * N + j);
-    g0r[i] = MGQP_LDG(io.g0 + i);
-  }
   double c1 = 0.0;
 #pragma unroll
   for (int i = 0; i < N; i++) c1 = d_add(c1, L[i][i]);
@@ -449,26 +463,41 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           double psi = 0.0;
           unsigned long long elig = ~act & excl;
           bool picked = false;
-#pragma unroll 3
-          for (int i = 0; i < m; i++) {
-            const int c = cidx[i];
-            double sum;
-            if (c != LN_DENSE && finite) {
-              // c >= 0: the single nonzero; c == EMPTY: an all-zero column (civ = 0, row 0)
-              sum = d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c]));
-            } else {
-              sum = 0.0;
+          if (!has_dense && finite) {
+            // every column is (row, value) or empty: s_i = (0.0 + v*x[row]) + ci0_i, bit for bit
+#pragma unroll 6
+            for (int i = 0; i < m; i++) {
+              const int c = cidx[i];
+              const double sum = d_add(d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c])), sci0[i]);
+              if (sum < 0.0) psi = d_add(psi, sum);  // adding +0.0 otherwise would not change psi
+              if (sum < ss && (elig & 1ull)) {
+                ss = sum;
+                ip = i;
+                picked = true;
+              }
+              elig >>= 1;
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < m; i++) {
+              const int c = cidx[i];
+              double sum;
+              if (c != LN_DENSE && finite) {
+                sum = d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c]));
+              } else {
+                sum = 0.0;
 #pragma unroll
-              for (int j = 0; j < N; j++) sum = mad<FMA>(MGQP_LDG(io.CI + j * m + i), x[j], sum);
+                for (int j = 0; j < N; j++) sum = mad<FMA>(MGQP_LDG(io.CI + j * m + i), x[j], sum);
+              }
+              sum = d_add(sum, sci0[i]);
+              psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
+              if (sum < ss && (elig & 1ull)) {
+                ss = sum;
+                ip = i;
+                picked = true;
+              }
+              elig >>= 1;
             }
-            sum = d_add(sum, sci0[i]);
-            psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
-            if (sum < ss && (elig & 1ull)) {
-              ss = sum;
-              ip = i;
-              picked = true;
-            }
-            elig >>= 1;
           }
           if (picked) s_ip = ss;
           if (l1) {
