@@ -38,7 +38,7 @@ struct TileView {
   int qpw;                               // QPs per warp = 32 / GW
   int oG, og0, oCE, oce0, oCI, oci0;     // input block, field-major; QP stride = natural size
   int oWork, wstride;                    // work block, QP-major
-  int wJ, wR, wx, wd, wr, wred;          // offsets inside one QP's work block
+  int wJ, wR, wx, wd, wr, wred, wgc, wgs, wgx;  // offsets inside one QP's work block
   int ldJ, ldR;
   int total;                             // doubles per warp (multiple of 2)
 };
@@ -69,6 +69,9 @@ MGQP_HOST inline TileView make_tile_view(int n, int p, int m, int gw) {
   tv.wd = w;   w += n;
   tv.wr = w;   w += n;
   tv.wred = w; w += gw;
+  tv.wgc = w;  w += gw;  // Givens coefficients of the add_constraint sweep, one rotation per lane
+  tv.wgs = w;  w += gw;
+  tv.wgx = w;  w += gw;
   tv.wstride = mgqp_even(w) + 2;  // +2 doubles skews consecutive QPs across banks
   tv.total = mgqp_even(o + tv.qpw * tv.wstride);
   return tv;
@@ -134,6 +137,9 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   double* sd = wk + tv.wd;
   double* sr = wk + tv.wr;
   double* sred = wk + tv.wred;
+  double* sgc = wk + tv.wgc;
+  double* sgs = wk + tv.wgs;
+  double* sgx = wk + tv.wgx;
 
   // ordered (ascending-index) sum of one value per lane, replicated to the whole group
   auto osum = [&](double v) -> double {
@@ -279,34 +285,73 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   auto add_constraint = [&](bool doit) -> bool {
     const int jlo = doit ? iq + 1 : n;
     const int jmin = wp_min(jlo);
-    double carry = (n > 0) ? sd[n - 1] : 0.0;  // current value of d[j]
+    // (1) the serial part of the sweep is only the chain of hypotenuses: `distance` uses |a|, |b|,
+    // so h_j = distance(d[j-1], h_{j+1}) needs neither the signs nor the divisions of rotation j+1.
+    // Every lane of the group runs the chain; lane j keeps h_j.
+    double carry = (n > 0) ? d_abs(sd[n - 1]) : 0.0;
+    double hreg = 1.0;
+    unsigned skipm = 0u;
     MGQP_UNROLL1
     for (int j = n - 1; j >= jmin; j--) {
       if (j >= jlo) {
-        double cc = sd[j - 1], ss = carry, xny = 0.0, diag = 0.0;
-        if (gi_givens(cc, ss, xny, diag)) {
-          carry = diag;
-          if (in_n) {
-            const double t1 = sJ[li * ldJ + j - 1], t2 = sJ[li * ldJ + j];
-            const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
-            sJ[li * ldJ + j - 1] = n1;
-            sJ[li * ldJ + j] = d_sub(d_mul(xny, d_add(t1, n1)), t2);
-          }
+        const double h = gi_distance(sd[j - 1], carry);
+        if (d_abs(h) < MGQP_EPS) {
+          skipm |= 1u << j;
+          carry = d_abs(sd[j - 1]);
         } else {
-          carry = cc;  // rotation skipped: d[j-1] keeps its value
+          if (li == j) hreg = h;
+          carry = h;
         }
       }
     }
+    // (2) lane j turns (d[j-1], incoming d[j], h_j) into the rotation's (c, s, s/(1+c)) with the
+    // reference's sign normalisation; the incoming d[j] is what rotation j+1 leaves behind.
+    const bool myrot = li >= jlo && li <= n - 1 && !((skipm >> li) & 1u);
+    const double dprev = (li > 0 && in_n) ? sd[li - 1] : 0.0;
+    double c = d_div(dprev, hreg);
+    const double dnew = ((skipm >> li) & 1u) ? dprev : ((c < 0.0) ? -hreg : hreg);  // new d[li-1]
+    const double dnext = wp_shfl_down(dnew, 1, GW);
+    const double din = (li == n - 1) ? sd[n - 1] : dnext;
+    double sn = d_div(din, hreg);
+    if (c < 0.0) {
+      c = -c;
+      sn = -sn;
+    }
+    if (myrot) {
+      sgc[li] = c;
+      sgs[li] = sn;
+      sgx[li] = d_div(sn, d_add(1.0, c));
+    }
+    const double dl_rot = wp_shfl(dnew, jlo & (GW - 1), GW);
+    const double dlast = (jlo <= n - 1) ? dl_rot : sd[iq < n ? iq : 0];
+    wp_sync();
+    // (3) lane k streams row k of J right to left through all rotations; no synchronisation needed
+    if (in_n) {
+      double t2 = sJ[li * ldJ + n - 1];
+      MGQP_UNROLL1
+      for (int j = n - 1; j >= jlo; j--) {
+        const double t1 = sJ[li * ldJ + j - 1];
+        if (!((skipm >> j) & 1u)) {
+          const double n1 = d_add(d_mul(t1, sgc[j]), d_mul(t2, sgs[j]));
+          sJ[li * ldJ + j] = d_sub(d_mul(sgx[j], d_add(t1, n1)), t2);
+          t2 = n1;
+        } else {
+          sJ[li * ldJ + j] = t2;
+          t2 = t1;
+        }
+      }
+      if (jlo <= n - 1) sJ[li * ldJ + jlo - 1] = t2;
+    }
     bool ok = true;
     if (doit) {
-      // column iq of R <- d[0..iq]   (d[iq] is the carried pivot)
+      // column iq of R <- d[0..iq]   (d[iq] is what the last rotation left)
       if (li < iq) sR[li * ldR + iq] = dv;
-      if (li == iq) sR[li * ldR + iq] = carry;
+      if (li == iq) sR[li * ldR + iq] = dlast;
       iq++;
-      if (d_abs(carry) <= d_mul(MGQP_EPS, R_norm)) {
+      if (d_abs(dlast) <= d_mul(MGQP_EPS, R_norm)) {
         ok = false;
       } else {
-        R_norm = (R_norm < d_abs(carry)) ? d_abs(carry) : R_norm;
+        R_norm = (R_norm < d_abs(dlast)) ? d_abs(dlast) : R_norm;
       }
     }
     wp_sync();
