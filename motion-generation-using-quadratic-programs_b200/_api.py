@@ -130,13 +130,6 @@ def kernel_launch_count() -> int:
 
 
 # ------------------------------------------------------------------ device-resident batches
-def _stride(t, natural: int) -> int:
-    """Element stride between QPs of a [B, ...] tensor (0 for an un-batched, broadcast field)."""
-    if t.shape[0] == 1 and natural > 0 and t.stride(0) != natural:
-        return 0
-    return t.stride(0)
-
-
 def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = False, max_iter: int = 0,
                            flags: int = 0, stream=None, out: Optional[QPResult] = None) -> QPResult:
     """Solve a batch of QPs held in CUDA tensors (float64).
@@ -162,7 +155,7 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
             raise ValueError("all inputs must be float64")
         if t.shape[0] not in (1, B):
             raise ValueError("leading dimensions must be B or 1")
-        ts.append(t if t[0].is_contiguous() or t.numel() == 0 else t.contiguous())
+        ts.append(t if t.numel() == 0 or t[0].is_contiguous() else t.contiguous())
     G, g0, CE, ce0, CI, ci0 = ts
     if out is None:
         x = torch.empty((B, n), dtype=torch.float64, device=dev)
@@ -174,6 +167,10 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
             A = torch.empty((B, p + m), dtype=torch.int32, device=dev)
             iters = torch.empty((B,), dtype=torch.int32, device=dev)
         out = QPResult(x, f, status, iq, A, iters)
+    if B == 0:
+        return out
+    if p > n:
+        raise ValueError(f"p = {p} equalities on n = {n} variables (the reference indexes R out of bounds there)")
     d = mgqp_batch()
     d.n, d.p, d.m, d.batch = n, p, m, B
     nat = (n * n, n, n * p, p, n * m, m)
@@ -268,8 +265,7 @@ def solve_quadprog(G, g0, CE, ce0, CI, ci0, x=None, *, device: int = 0) -> float
     """Single QP, reference semantics (QuadProg++.hh:69-72).
 
     ``G`` (float64 ndarray, n*n) is overwritten by its Cholesky factor; ``x`` (optional float64
-    ndarray of length n) receives the solution, which is also available as ``solve_quadprog.x``
-    of the call through the returned value's companion: use ``solve_quadprog_x`` if you need both.
+    ndarray of length n) receives the solution (also kept as ``solve_quadprog.last_x``).
     Returns the cost, ``math.inf`` if infeasible.
     """
     G_arr = np.asarray(G)

@@ -117,6 +117,25 @@ def test_mpc_shape_against_reference_binary_and_oracle(gpu, restatement):
     assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), "C4")
 
 
+def test_empty_batch_and_argument_errors(gpu):
+    import torch
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device="cuda:0")
+    r = gpu.solve_quadprog_batched(z(0, 3, 3), z(0, 3), z(0, 3, 1), z(0, 1), z(0, 3, 2), z(0, 2))
+    assert r.x.shape == (0, 3) and r.status.numel() == 0
+    with pytest.raises(ValueError, match="equalities"):          # p > n: the reference indexes R out of bounds there
+        gpu.solve_quadprog_batched(z(4, 2, 2), z(4, 2), z(4, 2, 3), z(4, 3), z(4, 2, 0), z(4, 0))
+    with pytest.raises(gpu.LogicError, match="The matrix CI is incompatible"):
+        gpu.solve_quadprog_batched(z(4, 2, 2), z(4, 2), z(4, 2, 0), z(4, 0), z(4, 3, 5), z(4, 5))
+
+
+def test_lane_kernel_shape_limits(gpu, restatement):
+    """n = 8 with m = 64 is the largest shape of the one-QP-per-lane family; m = 65 must fall back."""
+    for m in (63, 64, 65):
+        b = workloads.make_random(777, 8, 2, m, seed=m, box=True)
+        assert gpu.plan(8, 2, m)[0] == (1 if m <= 64 else 8)
+        assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), f"m{m}")
+
+
 def test_tail_and_tiny_batches(gpu, restatement):
     for B in (1, 2, 3, 4, 5, 7, 63):
         b = workloads.make("C2", B, seed=B)

@@ -15,7 +15,7 @@ for flags in (0, 8):
         print(f"flags={flags} chunk={chunk}: {dt*1e3:.1f} ms  {B/dt:.3e} QP/s")
 # device-resident small batches
 t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in b.fields()]
-for nb in ():
+for nb in (20000, 81920, 400000):
     tt = [x[:nb] for x in t]
     for flags in (0, 8):
         out = mgqp_b200.solve_quadprog_batched(*tt, flags=flags)
