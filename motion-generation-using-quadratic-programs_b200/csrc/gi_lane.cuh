@@ -23,14 +23,13 @@
 // results are bit-identical to QuadProg++ by construction (no cross-lane arithmetic at all).
 //
 // The set-up (Cholesky of G, J = L^-T, x0 = -G^-1 g0) is fully unrolled over the compile-time N and
-// lives in registers: G and g0 go from global memory straight into registers, only J is written to
-// the slot.  The 49 + 21 + 14 IEEE divisions of that phase are independent across rows, which is
+// lives in registers: G and g0 go from global memory straight into registers; J never leaves them.  The 49 + 21 + 14 IEEE divisions of that phase are independent across rows, which is
 // where a lone warp per scheduler gets its instruction-level parallelism from.
 //
 // Slot layout (doubles; the lane stride is odd so the 16 lanes of a half warp hit 16 distinct
 // 8-byte bank pairs whenever they address the same element):
-//   J[N*N] | R (upper Hessenberg, packed) | d[N] (doubles as the x mirror during scans) | r[N] |
-//   u[N+1] | u_old[N+1] | civ[m] | ci0[m] | int8: A[N+1], A_old[N+1], cidx[m]
+//   R (upper Hessenberg, packed) | d[N] (doubles as the x mirror during scans) | r[N] | u[N+1] |
+//   civ[m] | ci0[m] | int8: A[N+1], A_old[N+1], cidx[m]          (J and u_old live in registers)
 #pragma once
 #include "warp_prims.cuh"
 
@@ -64,24 +63,23 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
   LaneView v;
   v.n = n; v.p = p; v.m = m;
   int o = 0;
-  v.oJ = o;     o += n * n;
+  v.oJ = o;     /* J lives in registers */
   v.oR = o;     o += lane_rh_size(n);
   v.od = o;     o += n;
   v.orr = o;    o += n;
   v.ou = o;     o += n + 1;
-  v.ouold = o;  o += n + 1;
+  v.ouold = o;  /* u_old lives in registers */
   v.ociv = o;   o += m;
   v.oci0 = o;   o += m;
+  // the civ|ci0 area doubles as set-up scratch (L | y | x | g0), the R|d|r|u area as scratch for J
+  if (2 * m < n * n + 3 * n) o += n * n + 3 * n - 2 * m;
   v.oByte = o;
   v.bA = 0;
   v.bAold = n + 1;
   v.bcidx = 2 * (n + 1);
   const int bytes = 2 * (n + 1) + m;
   o += (bytes + 7) / 8;
-  if ((o & 1) == 0) o++;
-  // odd is enough for conflict-free same-element access; == 1 (mod 16) additionally spreads the
-  // two half warps over disjoint bank pairs
-  while ((o & 15) != 1 && (o & 15) != 9) o += 2;
+  if ((o & 1) == 0) o++;  // odd stride: the 16 lanes of a half warp land on 16 distinct 8-byte bank pairs
   v.stride = o;
   return v;
 }
@@ -100,6 +98,32 @@ MGQP_DEV double ln_distance(double a, double b) {
   return d_mul(a1, d_sqrt(2.0));
 }
 
+// (c, s) -> normalised rotation coefficients exactly as add_constraint / delete_constraint derive
+// them (Appendix A).  One shared, non-inlined copy: it holds four IEEE divisions and a square root,
+// and the unrolled sweeps call it from twelve places.  valid == 0 <=> the reference `continue`s.
+struct LaneGivens {
+  double c, s, xny, diag;
+  int valid;
+};
+MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
+  LaneGivens g;
+  const double h = ln_distance(cc, ss);
+  g.valid = !(d_abs(h) < MGQP_EPS);
+  ss = d_div(ss, h);
+  cc = d_div(cc, h);
+  if (cc < 0.0) {
+    cc = -cc;
+    ss = -ss;
+    g.diag = -h;
+  } else {
+    g.diag = h;
+  }
+  g.c = cc;
+  g.s = ss;
+  g.xny = d_div(ss, d_add(1.0, cc));
+  return g;
+}
+
 struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
 };
@@ -108,12 +132,10 @@ template <int N, bool FMA>
 MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int max_iter, double* x_out,
                             double& f_out, int& status_out, int& iq_out, int& iters_out) {
   const int p = v.p, m = v.m;
-  double* J = S + v.oJ;
   double* R = S + v.oR;
   double* sd = S + v.od;  // d; reused as the smem mirror of x while scanning
   double* sr = S + v.orr;
   double* su = S + v.ou;
-  double* suold = S + v.ouold;
   double* civ = S + v.ociv;
   double* sci0 = S + v.oci0;
   signed char* Bt = reinterpret_cast<signed char*>(S + v.oByte);
@@ -129,19 +151,120 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll
   for (int i = 0; i < N; i++) { x[i] = 0.0; z[i] = 0.0; np[i] = 0.0; dd[i] = 0.0; xold[i] = 0.0; }
 
-  // G and g0 first: their loads are in flight while the constraint columns are being classified
-  double L[N][N], g0r[N];
+  // ---------------------------------------------------------------- set-up
+  // Cholesky of G, J = L^-T and x0 = -G^-1 g0 run out of shared-memory scratch that the constraint
+  // data will occupy later (L | y | x | g0 in the civ/ci0 area, J in the R|d|r|u area), with the
+  // outer loops rolled and the independent rows unrolled: a fully unrolled register version was
+  // 4 000 instructions of straight-line code and made the kernel instruction-fetch bound.
+  double* Ls = S + v.ociv;
+  double* ys = Ls + N * N;
+  double* xs = ys + N;
+  double* g0s = xs + N;
+  double* Js = S + v.oR;
 #pragma unroll
-  for (int i = 0; i < N; i++) {
+  for (int i = 0; i < N * N; i++) Ls[i] = MGQP_LDG(io.G + i);
 #pragma unroll
-    for (int j = 0; j < N; j++) L[i][j] = MGQP_LDG(io.G + i * N + j);
-    g0r[i] = MGQP_LDG(io.g0 + i);
+  for (int i = 0; i < N; i++) g0s[i] = MGQP_LDG(io.g0 + i);
+  double c1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; i++) c1 = d_add(c1, Ls[i * N + i]);
+
+  bool fail = false;
+  double bad_pivot = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < N && !fail; i++) {
+    double sum[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) sum[j] = Ls[i * N + j];
+#pragma unroll 1
+    for (int k = i - 1; k >= 0; k--) {
+      const double lik = Ls[i * N + k];
+#pragma unroll
+      for (int j = 0; j < N; j++)
+        if (j >= i) sum[j] = msub<FMA>(sum[j], lik, Ls[j * N + k]);
+    }
+    double piv = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+      if (j == i) piv = sum[j];
+    if (piv <= 0.0) {
+      fail = true;
+      bad_pivot = piv;
+    } else {
+      const double dii = d_sqrt(piv);
+      Ls[i * N + i] = dii;
+#pragma unroll
+      for (int j = 0; j < N; j++)
+        if (j > i) {
+          const double val = d_div(sum[j], dii);
+          Ls[j * N + i] = val;
+          Ls[i * N + j] = val;
+        }
+    }
   }
 
-  // ---------------------------------------------------------------- inequality columns: classify
+  if (fail) {
+    status = 2;
+    f = bad_pivot;
+  } else {
+    // J = L^-T: all N rows (row i = forward_elimination(L, e_i)) advance together, column by column
+    double c2 = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < N; r++) {
+      double acc[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) acc[i] = (i == r) ? 1.0 : 0.0;
+#pragma unroll 1
+      for (int j = 0; j < r; j++) {
+        const double lrj = Ls[r * N + j];
+#pragma unroll
+        for (int i = 0; i < N; i++) acc[i] = msub<FMA>(acc[i], lrj, Js[i * N + j]);
+      }
+      const double lrr = Ls[r * N + r];
+#pragma unroll
+      for (int i = 0; i < N; i++) Js[i * N + r] = d_div(acc[i], lrr);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) c2 = d_add(c2, Js[i * N + i]);
+    // x = -G^-1 g0 (cholesky_solve: forward then backward elimination), f = 0.5 g0.x
+    ys[0] = d_div(g0s[0], Ls[0]);
+#pragma unroll 1
+    for (int i = 1; i < N; i++) {
+      double a = g0s[i];
+#pragma unroll 1
+      for (int j = 0; j < i; j++) a = msub<FMA>(a, Ls[i * N + j], ys[j]);
+      ys[i] = d_div(a, Ls[i * N + i]);
+    }
+    xs[N - 1] = d_div(ys[N - 1], Ls[(N - 1) * N + (N - 1)]);
+#pragma unroll 1
+    for (int i = N - 2; i >= 0; i--) {
+      double a = ys[i];
+#pragma unroll 1
+      for (int j = i + 1; j < N; j++) a = msub<FMA>(a, Ls[i * N + j], xs[j]);
+      xs[i] = d_div(a, Ls[i * N + i]);
+    }
+    double fs = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      x[i] = -xs[i];
+      fs = mad<FMA>(g0s[i], x[i], fs);
+    }
+    f = d_mul(0.5, fs);
+    // J moves into REGISTERS for the whole solve: every access below has compile-time indices (the
+    // Givens sweeps are unrolled over the column index and predicated on the lane's own iq), which
+    // keeps J out of shared memory (6 resident warps per SM instead of 4) and removes ~100
+    // shared-memory loads from every iteration.
+    double Jr[N][N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = 0; j < N; j++) Jr[i][j] = Js[i * N + j];
+
+    // ---------------------------------------------------------------- inequality columns: classify
+    // (after the set-up: it overwrites the scratch)
   // Row-major sweep of this QP's CI straight from global memory (each 32-byte sector is fetched from
   // HBM once and then served by L1 for the lane's next loads); ci0 is parked in the slot.
-  {
+    {
 #pragma unroll 1
     for (int i = 0; i < m; i++) {
       cidx[i] = LN_EMPTY;
@@ -160,10 +283,10 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     };
     const int nm = N * m;
     if (((nm & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.CI) & 15ull) == 0ull)) {
-      // 16-byte loads, 8 in flight: a 32-byte sector is consumed by two back-to-back loads of the
+      // 16-byte loads, 6 in flight per lane: a 32-byte sector is consumed by two back-to-back loads of the
       // same lane instead of living in L1 across loop iterations
       int j = 0, i = 0;
-#pragma unroll 12
+#pragma unroll 6
       for (int e = 0; e < nm; e += 2) {
         double a0, a1;
         MGQP_LDG2(io.CI + e, a0, a1);
@@ -181,7 +304,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       }
     }
     if (((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.ci0) & 15ull) == 0ull)) {
-#pragma unroll 11
+#pragma unroll 4
       for (int i = 0; i < m; i += 2) {
         double a0, a1;
         MGQP_LDG2(io.ci0 + i, a0, a1);
@@ -194,98 +317,129 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     }
   }
 
-  // ---------------------------------------------------------------- set-up in registers
-  double c1 = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; i++) c1 = d_add(c1, L[i][i]);
-
-  bool fail = false;
-  double bad_pivot = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-#pragma unroll
-    for (int j = i; j < N; j++) {
-      double sum = L[i][j];
-#pragma unroll
-      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, L[i][k], L[j][k]);
-      if (i == j) {
-        if (!fail && sum <= 0.0) {
-          fail = true;
-          bad_pivot = sum;
-        }
-        L[i][i] = d_sqrt(sum);
-      } else {
-        L[j][i] = d_div(sum, L[i][i]);
-      }
-    }
-#pragma unroll
-    for (int k = i + 1; k < N; k++) L[i][k] = L[k][i];
-  }
-
-  if (fail) {
-    status = 2;
-    f = bad_pivot;
-  } else {
-    // J = L^-T (row i = forward_elimination(L, e_i)); c2 = trace(J)
-    double c2 = 0.0;
-    {
-      double Jr[N][N];
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-#pragma unroll
-        for (int r = 0; r < N; r++) {
-          double acc = (r == i) ? 1.0 : 0.0;
-#pragma unroll
-          for (int j = 0; j < r; j++) acc = msub<FMA>(acc, L[r][j], Jr[i][j]);
-          Jr[i][r] = d_div(acc, L[r][r]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        c2 = d_add(c2, Jr[i][i]);
-#pragma unroll
-        for (int r = 0; r < N; r++) J[i * N + r] = Jr[i][r];
-      }
-    }
-    // x = -G^-1 g0 (cholesky_solve: forward then backward elimination), f = 0.5 g0.x
-    {
-      double y[N], xx[N];
-      y[0] = d_div(g0r[0], L[0][0]);
-#pragma unroll
-      for (int i = 1; i < N; i++) {
-        double a = g0r[i];
-#pragma unroll
-        for (int j = 0; j < i; j++) a = msub<FMA>(a, L[i][j], y[j]);
-        y[i] = d_div(a, L[i][i]);
-      }
-      xx[N - 1] = d_div(y[N - 1], L[N - 1][N - 1]);
-#pragma unroll
-      for (int i = N - 2; i >= 0; i--) {
-        double a = y[i];
-#pragma unroll
-        for (int j = i + 1; j < N; j++) a = msub<FMA>(a, L[i][j], xx[j]);
-        xx[i] = d_div(a, L[i][i]);
-      }
-      double fs = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        x[i] = -xx[i];
-        fs = mad<FMA>(g0r[i], x[i], fs);
-      }
-      f = d_mul(0.5, fs);
-    }
 #pragma unroll 1
     for (int i = 0; i < lane_rh_size(N); i++) R[i] = 0.0;
 
     double R_norm = 1.0;
+    const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
+    unsigned long long act = 0ull, excl = ~0ull;  // iai[i] == -1  /  iaexcl[i]
+    int ip = 0, e = 0;                             // e = next equality constraint to add
+    double ss = 0.0, s_ip = 0.0;
+    bool need_scan = true, l1 = true, done = false;
+    double uold[N + 1];
+#pragma unroll
+    for (int i = 0; i <= N; i++) uold[i] = 0.0;
 
-    // d = J^T np (registers + smem copy), z = J[:, iq:] d[iq:], r = R^-1 d
-    auto direction = [&]() {
+    // One pass of this loop = one step-direction computation: first the p equality constraints
+    // (Appendix A, "for each equality"), then the active-set iteration proper.  add_constraint and
+    // delete_constraint each appear exactly once in the code.
+#pragma unroll 1
+    while (!done) {
+      const bool eqm = e < p;
+      if (eqm) {
+#pragma unroll
+        for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CE + j * p + e);
+      } else if (need_scan) {
+        // ------------------------------------------------ step 1 / 2: scan, choose ip
+        if (l1) {
+          excl = ~0ull;
+          ss = 0.0;
+          ip = 0;
+        }
+        bool finite = true;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          sd[j] = x[j];  // x mirror (d is dead between add_constraint and the next direction)
+          finite = finite && (d_abs(x[j]) < INF);
+        }
+        double psi = 0.0;
+        unsigned long long elig = ~act & excl;
+        bool picked = false;
+        if (!has_dense && finite) {
+          // every column is (row, value) or empty: s_i = (0.0 + v*x[row]) + ci0_i, bit for bit
+#pragma unroll 6
+          for (int i = 0; i < m; i++) {
+            const int c = cidx[i];
+            const double sum = d_add(d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c])), sci0[i]);
+            if (sum < 0.0) psi = d_add(psi, sum);  // adding +0.0 otherwise would not change psi
+            if (sum < ss && (elig & 1ull)) {
+              ss = sum;
+              ip = i;
+              picked = true;
+            }
+            elig >>= 1;
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < m; i++) {
+            const int c = cidx[i];
+            double sum;
+            if (c != LN_DENSE && finite) {
+              sum = d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c]));
+            } else {
+              sum = 0.0;
+#pragma unroll
+              for (int j = 0; j < N; j++) sum = mad<FMA>(MGQP_LDG(io.CI + j * m + i), x[j], sum);
+            }
+            sum = d_add(sum, sci0[i]);
+            psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
+            if (sum < ss && (elig & 1ull)) {
+              ss = sum;
+              ip = i;
+              picked = true;
+            }
+            elig >>= 1;
+          }
+        }
+        if (picked) s_ip = ss;
+        if (l1) {
+          if (d_abs(psi) <= thr) {
+            done = true;
+          } else {
+#pragma unroll
+            for (int i = 0; i <= N; i++)
+              if (i < iq) {
+                uold[i] = su[i];
+                Aold[i] = A[i];
+              }
+#pragma unroll
+            for (int i = 0; i < N; i++) xold[i] = x[i];
+          }
+        }
+        if (!done) {
+          if (ss >= 0.0) {
+            done = true;
+          } else {
+            const int c = cidx[ip];
+            if (c == LN_DENSE) {
+#pragma unroll
+              for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CI + j * m + ip);
+            } else {
+              const double a = civ[ip];
+#pragma unroll
+              for (int j = 0; j < N; j++) np[j] = (j == c) ? a : 0.0;
+            }
+            su[iq] = 0.0;
+            A[iq] = (signed char)ip;
+            need_scan = false;
+          }
+        }
+        if (done) break;
+      }
+      if (!eqm) {
+        steps++;
+        if (steps > max_iter) {
+          status = 4;
+          break;
+        }
+      }
+
+      // ------------------------------------------------ step 2a: d = J^T np, z = J[:, iq:] d[iq:], r = R^-1 d
 #pragma unroll
       for (int i = 0; i < N; i++) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; j++) s = mad<FMA>(J[j * N + i], np[j], s);
+        for (int j = 0; j < N; j++) s = mad<FMA>(Jr[j][i], np[j], s);
         dd[i] = s;
         sd[i] = s;
       }
@@ -294,7 +448,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < N; j++)
-          if (j >= iq) s = mad<FMA>(J[i * N + j], dd[j], s);
+          if (j >= iq) s = mad<FMA>(Jr[i][j], dd[j], s);
         z[i] = s;
       }
 #pragma unroll 1
@@ -304,242 +458,31 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
         for (int j = i + 1; j < iq; j++) s = mad<FMA>(R[MGQP_RH(i, j)], sr[j], s);
         sr[i] = d_div(d_sub(sd[i], s), R[MGQP_RH(i, i)]);
       }
-    };
-    auto dot_zz = [&]() {
-      double s = 0.0;
+      double zz = 0.0, znp = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; i++) s = mad<FMA>(z[i], z[i], s);
-      return s;
-    };
-    auto dot_znp = [&]() {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i++) s = mad<FMA>(z[i], np[i], s);
-      return s;
-    };
-    auto dot_npx = [&]() {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i++) s = mad<FMA>(np[i], x[i], s);
-      return s;
-    };
-
-    // add_constraint (Appendix A): Givens sweep j = n-1 .. iq+1 on d, columns j-1, j of J
-    auto add_constraint = [&]() -> bool {
-#pragma unroll 1
-      for (int j = N - 1; j >= iq + 1; j--) {
-        double cc = sd[j - 1], ss = sd[j];
-        const double h = ln_distance(cc, ss);
-        if (d_abs(h) < MGQP_EPS) continue;
-        sd[j] = 0.0;
-        ss = d_div(ss, h);
-        cc = d_div(cc, h);
-        if (cc < 0.0) {
-          cc = -cc;
-          ss = -ss;
-          sd[j - 1] = -h;
-        } else {
-          sd[j - 1] = h;
-        }
-        const double xny = d_div(ss, d_add(1.0, cc));
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-          const double t1 = J[k * N + j - 1], t2 = J[k * N + j];
-          const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
-          J[k * N + j - 1] = n1;
-          J[k * N + j] = d_sub(d_mul(xny, d_add(t1, n1)), t2);
-        }
+      for (int i = 0; i < N; i++) {
+        zz = mad<FMA>(z[i], z[i], zz);
+        znp = mad<FMA>(z[i], np[i], znp);
       }
-      iq++;
-#pragma unroll 1
-      for (int i = 0; i < iq; i++) R[MGQP_RH(i, iq - 1)] = sd[i];
-      const double dl = d_abs(sd[iq - 1]);
-      if (dl <= d_mul(MGQP_EPS, R_norm)) return false;
-      R_norm = (R_norm < dl) ? dl : R_norm;
-      return true;
-    };
 
-    // delete_constraint(l) (Appendix A).  A/u have a valid slot at index iq (the pending pair).
-    auto delete_constraint = [&](int l) {
-      int qq = 0;
-#pragma unroll 1
-      for (int i = p; i < iq; i++)
-        if (A[i] == l) {
-          qq = i;
-          break;
-        }
-#pragma unroll 1
-      for (int i = qq; i < iq - 1; i++) {
-        A[i] = A[i + 1];
-        su[i] = su[i + 1];
-        // rows below i+1 are structurally zero in both columns: nothing to move there
-#pragma unroll 1
-        for (int j = 0; j <= i + 1; j++) R[MGQP_RH(j, i)] = R[MGQP_RH(j, i + 1)];
-      }
-      A[iq - 1] = A[iq];
-      su[iq - 1] = su[iq];
-      A[iq] = 0;
-      su[iq] = 0.0;
-#pragma unroll 1
-      for (int j = 0; j < iq; j++) R[MGQP_RH(j, iq - 1)] = 0.0;
-      iq--;
-      if (iq == 0) return;
-#pragma unroll 1
-      for (int j = qq; j < iq; j++) {
-        double cc = R[MGQP_RH(j, j)], ss = R[MGQP_RH(j + 1, j)];
-        const double h = ln_distance(cc, ss);
-        if (d_abs(h) < MGQP_EPS) continue;
-        cc = d_div(cc, h);
-        ss = d_div(ss, h);
-        R[MGQP_RH(j + 1, j)] = 0.0;
-        if (cc < 0.0) {
-          R[MGQP_RH(j, j)] = -h;
-          cc = -cc;
-          ss = -ss;
-        } else {
-          R[MGQP_RH(j, j)] = h;
-        }
-        const double xny = d_div(ss, d_add(1.0, cc));
-#pragma unroll 1
-        for (int k = j + 1; k < iq; k++) {
-          const double t1 = R[MGQP_RH(j, k)], t2 = R[MGQP_RH(j + 1, k)];
-          const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
-          R[MGQP_RH(j, k)] = n1;
-          R[MGQP_RH(j + 1, k)] = d_sub(d_mul(xny, d_add(t1, n1)), t2);
-        }
+      // ------------------------------------------------ step 2b / 2c: step lengths, take the step
+      bool do_add = false, do_del = false, partial = false;
+      int del_l = 0;
+      if (eqm) {
+        double npx = 0.0;
 #pragma unroll
-        for (int k = 0; k < N; k++) {
-          const double t1 = J[k * N + j], t2 = J[k * N + j + 1];
-          const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
-          J[k * N + j] = n1;
-          J[k * N + j + 1] = d_sub(d_mul(xny, d_add(n1, t1)), t2);
-        }
-      }
-    };
-
-    // ---------------------------------------------------------------- equality constraints
-    bool dead = false;
+        for (int i = 0; i < N; i++) npx = mad<FMA>(np[i], x[i], npx);
+        double t2 = 0.0;
+        if (d_abs(zz) > MGQP_EPS) t2 = d_div(d_sub(-npx, MGQP_LDG(io.ce0 + e)), znp);
+#pragma unroll
+        for (int k = 0; k < N; k++) x[k] = d_add(x[k], d_mul(t2, z[k]));
+        su[iq] = t2;
 #pragma unroll 1
-    for (int e = 0; e < p && !dead; e++) {
-#pragma unroll
-      for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CE + j * p + e);
-      direction();
-      double t2 = 0.0;
-      if (d_abs(dot_zz()) > MGQP_EPS) t2 = d_div(d_sub(-dot_npx(), MGQP_LDG(io.ce0 + e)), dot_znp());
-#pragma unroll
-      for (int k = 0; k < N; k++) x[k] = d_add(x[k], d_mul(t2, z[k]));
-      su[iq] = t2;
-#pragma unroll 1
-      for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t2, sr[k]));
-      f = d_add(f, d_mul(d_mul(0.5, d_mul(t2, t2)), dot_znp()));
-      A[e] = (signed char)(-e - 1);
-      if (!add_constraint()) {
-        status = 3;
-        dead = true;
-      }
-    }
-
-    // ---------------------------------------------------------------- active-set iteration
-    if (!dead) {
-      const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
-      unsigned long long act = 0ull, excl = ~0ull;  // iai[i] == -1  /  iaexcl[i]
-      int ip = 0;
-      double ss = 0.0, s_ip = 0.0;
-      bool need_scan = true, l1 = true, done = false;
-#pragma unroll 1
-      while (!done) {
-        if (need_scan) {
-          if (l1) {
-            excl = ~0ull;
-            ss = 0.0;
-            ip = 0;
-          }
-          bool finite = true;
-#pragma unroll
-          for (int j = 0; j < N; j++) {
-            sd[j] = x[j];  // x mirror (d is dead between add_constraint and the next direction())
-            finite = finite && (d_abs(x[j]) < INF);
-          }
-          double psi = 0.0;
-          unsigned long long elig = ~act & excl;
-          bool picked = false;
-          if (!has_dense && finite) {
-            // every column is (row, value) or empty: s_i = (0.0 + v*x[row]) + ci0_i, bit for bit
-#pragma unroll 6
-            for (int i = 0; i < m; i++) {
-              const int c = cidx[i];
-              const double sum = d_add(d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c])), sci0[i]);
-              if (sum < 0.0) psi = d_add(psi, sum);  // adding +0.0 otherwise would not change psi
-              if (sum < ss && (elig & 1ull)) {
-                ss = sum;
-                ip = i;
-                picked = true;
-              }
-              elig >>= 1;
-            }
-          } else {
-#pragma unroll 1
-            for (int i = 0; i < m; i++) {
-              const int c = cidx[i];
-              double sum;
-              if (c != LN_DENSE && finite) {
-                sum = d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c]));
-              } else {
-                sum = 0.0;
-#pragma unroll
-                for (int j = 0; j < N; j++) sum = mad<FMA>(MGQP_LDG(io.CI + j * m + i), x[j], sum);
-              }
-              sum = d_add(sum, sci0[i]);
-              psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
-              if (sum < ss && (elig & 1ull)) {
-                ss = sum;
-                ip = i;
-                picked = true;
-              }
-              elig >>= 1;
-            }
-          }
-          if (picked) s_ip = ss;
-          if (l1) {
-            if (d_abs(psi) <= thr) {
-              done = true;
-            } else {
-#pragma unroll 1
-              for (int i = 0; i < iq; i++) {
-                suold[i] = su[i];
-                Aold[i] = A[i];
-              }
-#pragma unroll
-              for (int i = 0; i < N; i++) xold[i] = x[i];
-            }
-          }
-          if (!done) {
-            if (ss >= 0.0) {
-              done = true;
-            } else {
-              const int c = cidx[ip];
-              if (c == LN_DENSE) {
-#pragma unroll
-                for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CI + j * m + ip);
-              } else {
-                const double a = civ[ip];
-#pragma unroll
-                for (int j = 0; j < N; j++) np[j] = (j == c) ? a : 0.0;
-              }
-              su[iq] = 0.0;
-              A[iq] = (signed char)ip;
-              need_scan = false;
-            }
-          }
-        }
-        if (done) break;
-
-        steps++;
-        if (steps > max_iter) {
-          status = 4;
-          break;
-        }
-        direction();
+        for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t2, sr[k]));
+        f = d_add(f, d_mul(d_mul(0.5, d_mul(t2, t2)), znp));
+        A[iq] = (signed char)(-e - 1);  // A[e]: iq == e while the equalities are being added
+        do_add = true;
+      } else {
         int l = 0;
         double t1 = INF;
 #pragma unroll 1
@@ -553,8 +496,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           }
         }
         double t2;
-        const double znp = dot_znp();
-        if (d_abs(dot_zz()) > MGQP_EPS) {
+        if (d_abs(zz) > MGQP_EPS) {
           t2 = d_div(-s_ip, znp);
           if (t2 < 0.0) t2 = INF;
         } else {
@@ -567,44 +509,149 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           break;
         }
         if (t2 >= INF) {
+          // dual step only: drop constraint l, stay on ip
 #pragma unroll 1
           for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t, sr[k]));
           su[iq] = d_add(su[iq], t);
           act &= ~(1ull << l);
-          delete_constraint(l);
-          continue;
-        }
+          do_del = true;
+          del_l = l;
+        } else {
 #pragma unroll
-        for (int k = 0; k < N; k++) x[k] = d_add(x[k], d_mul(t, z[k]));
-        f = d_add(f, d_mul(d_mul(t, znp), d_add(d_mul(0.5, t), su[iq])));
+          for (int k = 0; k < N; k++) x[k] = d_add(x[k], d_mul(t, z[k]));
+          f = d_add(f, d_mul(d_mul(t, znp), d_add(d_mul(0.5, t), su[iq])));
 #pragma unroll 1
-        for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t, sr[k]));
-        su[iq] = d_add(su[iq], t);
-        if (d_abs(d_sub(t, t2)) < MGQP_EPS) {
-          if (!add_constraint()) {
-            excl &= ~(1ull << ip);
-            delete_constraint(ip);
-            act = 0ull;
-#pragma unroll 1
-            for (int i = p; i < iq; i++) {
-              A[i] = Aold[i];
-              su[i] = suold[i];
-              act |= 1ull << A[i];
-            }
-#pragma unroll
-            for (int i = 0; i < N; i++) x[i] = xold[i];
-            need_scan = true;
-            l1 = false;
+          for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t, sr[k]));
+          su[iq] = d_add(su[iq], t);
+          if (d_abs(d_sub(t, t2)) < MGQP_EPS) {
+            do_add = true;  // full step
           } else {
-            act |= 1ull << ip;
-            need_scan = true;
-            l1 = true;
+            act &= ~(1ull << l);  // partial step: drop l, stay on ip
+            do_del = true;
+            del_l = l;
+            partial = true;
           }
-          continue;
         }
-        act &= ~(1ull << l);
-        delete_constraint(l);
-        s_ip = d_add(dot_npx(), sci0[ip]);  // s[ip] = CI[:,ip].x + ci0[ip] with the new x
+      }
+
+      // ------------------------------------------------ add_constraint (Appendix A)
+      bool degenerate = false;
+      if (do_add) {
+#pragma unroll
+        for (int j = N - 1; j >= 1; j--) {
+          if (j >= iq + 1) {
+            const LaneGivens g = ln_givens(dd[j - 1], dd[j]);
+            if (g.valid) {
+              dd[j] = 0.0;
+              dd[j - 1] = g.diag;
+#pragma unroll
+              for (int k = 0; k < N; k++) {
+                const double t1 = Jr[k][j - 1], t2 = Jr[k][j];
+                const double n1 = d_add(d_mul(t1, g.c), d_mul(t2, g.s));
+                Jr[k][j - 1] = n1;
+                Jr[k][j] = d_sub(d_mul(g.xny, d_add(t1, n1)), t2);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) sd[i] = dd[i];
+        iq++;
+#pragma unroll 1
+        for (int i = 0; i < iq; i++) R[MGQP_RH(i, iq - 1)] = sd[i];
+        const double dl = d_abs(sd[iq - 1]);
+        bool ok = true;
+        if (dl <= d_mul(MGQP_EPS, R_norm)) ok = false;
+        else R_norm = (R_norm < dl) ? dl : R_norm;
+        if (eqm) {
+          if (!ok) {
+            status = 3;
+            break;
+          }
+          e++;
+        } else if (ok) {
+          act |= 1ull << ip;
+          need_scan = true;
+          l1 = true;
+        } else {
+          degenerate = true;
+          excl &= ~(1ull << ip);
+          do_del = true;
+          del_l = ip;
+        }
+      }
+
+      // ------------------------------------------------ delete_constraint(del_l) (Appendix A)
+      if (do_del) {
+        int qq = 0;
+#pragma unroll 1
+        for (int i = p; i < iq; i++)
+          if (A[i] == del_l) {
+            qq = i;
+            break;
+          }
+#pragma unroll 1
+        for (int i = qq; i < iq - 1; i++) {
+          A[i] = A[i + 1];
+          su[i] = su[i + 1];
+          // rows below i+1 are structurally zero in both columns: nothing to move there
+#pragma unroll 1
+          for (int j = 0; j <= i + 1; j++) R[MGQP_RH(j, i)] = R[MGQP_RH(j, i + 1)];
+        }
+        A[iq - 1] = A[iq];
+        su[iq - 1] = su[iq];
+        A[iq] = 0;
+        su[iq] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < iq; j++) R[MGQP_RH(j, iq - 1)] = 0.0;
+        iq--;
+        if (iq > 0) {
+#pragma unroll
+          for (int j = 0; j < N - 1; j++) {
+            if (j >= qq && j < iq) {
+              const LaneGivens g = ln_givens(R[MGQP_RH(j, j)], R[MGQP_RH(j + 1, j)]);
+              if (g.valid) {
+                R[MGQP_RH(j + 1, j)] = 0.0;
+                R[MGQP_RH(j, j)] = g.diag;
+#pragma unroll 1
+                for (int k = j + 1; k < iq; k++) {
+                  const double t1 = R[MGQP_RH(j, k)], t2 = R[MGQP_RH(j + 1, k)];
+                  const double n1 = d_add(d_mul(t1, g.c), d_mul(t2, g.s));
+                  R[MGQP_RH(j, k)] = n1;
+                  R[MGQP_RH(j + 1, k)] = d_sub(d_mul(g.xny, d_add(t1, n1)), t2);
+                }
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                  const double t1 = Jr[k][j], t2 = Jr[k][j + 1];
+                  const double n1 = d_add(d_mul(t1, g.c), d_mul(t2, g.s));
+                  Jr[k][j] = n1;
+                  Jr[k][j + 1] = d_sub(d_mul(g.xny, d_add(n1, t1)), t2);
+                }
+              }
+            }
+          }
+        }
+      }
+
+      if (degenerate) {
+        // restore the state saved at step 1 and go back to step 2 with the stale ss
+        act = 0ull;
+#pragma unroll
+        for (int i = 0; i <= N; i++)
+          if (i >= p && i < iq) {
+            A[i] = Aold[i];
+            su[i] = uold[i];
+            act |= 1ull << A[i];
+          }
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = xold[i];
+        need_scan = true;
+        l1 = false;
+      } else if (partial) {
+        double npx = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; i++) npx = mad<FMA>(np[i], x[i], npx);
+        s_ip = d_add(npx, sci0[ip]);  // s[ip] = CI[:,ip].x + ci0[ip] with the new x
       }
     }
   }
