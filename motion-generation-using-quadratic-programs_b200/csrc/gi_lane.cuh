@@ -40,7 +40,9 @@
 #ifdef MGQP_EMULATE
 #define MGQP_LDG(p) (*(p))
 #define MGQP_LDG2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
+#define MGQP_PREFETCH_L2(p) do { } while (0)
 #else
+#define MGQP_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define MGQP_LDG(p) __ldg(p)
 #define MGQP_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
 #endif
@@ -156,6 +158,17 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
   // data will occupy later (L | y | x | g0 in the civ/ci0 area, J in the R|d|r|u area), with the
   // outer loops rolled and the independent rows unrolled: a fully unrolled register version was
   // 4 000 instructions of straight-line code and made the kernel instruction-fetch bound.
+  // Pull this lane's constraint data towards L2 now; it is consumed right after the set-up (a
+  // whole-tile-ahead prefetch was evicted before use and doubled the DRAM traffic, this one is not).
+  {
+    const char* pc = reinterpret_cast<const char*>(io.CI);
+    const int bytes = N * m * 8;
+#pragma unroll 4
+    for (int o = 0; o < bytes; o += 128) MGQP_PREFETCH_L2(pc + o);
+    const char* p0 = reinterpret_cast<const char*>(io.ci0);
+#pragma unroll 1
+    for (int o = 0; o < m * 8; o += 128) MGQP_PREFETCH_L2(p0 + o);
+  }
   double* Ls = S + v.ociv;
   double* ys = Ls + N * N;
   double* xs = ys + N;
