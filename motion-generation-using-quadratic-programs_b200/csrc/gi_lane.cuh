@@ -86,7 +86,9 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
   return v;
 }
 
-enum { LN_EMPTY = -2, LN_DENSE = -1 };
+// per-column byte: bits 0-2 row of the single nonzero | ONE (a nonzero has been seen) | DENSE (more than
+// one) | EXCL (iaexcl == false) | ACT (iai == -1).  A column may be chosen iff byte < LN_EXCL.
+enum { LN_ROW = 0x07, LN_ONE = 0x10, LN_DENSE = 0x20, LN_EXCL = 0x40, LN_ACT = 0x80 };
 
 MGQP_DEV double ln_distance(double a, double b) {
   const double a1 = d_abs(a), b1 = d_abs(b);
@@ -143,7 +145,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
   signed char* Bt = reinterpret_cast<signed char*>(S + v.oByte);
   signed char* A = Bt + v.bA;
   signed char* Aold = Bt + v.bAold;
-  signed char* cidx = Bt + v.bcidx;
+  unsigned char* cidx = reinterpret_cast<unsigned char*>(Bt + v.bcidx);
   const double INF = d_inf();
 
   int status = 0, iq = 0, steps = 0;
@@ -280,16 +282,16 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     {
 #pragma unroll 1
     for (int i = 0; i < m; i++) {
-      cidx[i] = LN_EMPTY;
+      cidx[i] = 0;
       civ[i] = 0.0;
     }
     auto classify = [&](double a, int j, int i) {
       if (a != 0.0) {  // NaN counts as nonzero
-        if (cidx[i] == LN_EMPTY) {
-          cidx[i] = (signed char)j;
+        if (!(cidx[i] & LN_ONE)) {
+          cidx[i] = (unsigned char)(j | LN_ONE);
           civ[i] = a;
         } else {
-          cidx[i] = LN_DENSE;
+          cidx[i] |= LN_DENSE;
           has_dense = true;
         }
       }
@@ -335,7 +337,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 
     double R_norm = 1.0;
     const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
-    unsigned long long act = 0ull, excl = ~0ull;  // iai[i] == -1  /  iaexcl[i]
+    bool any_excl = false;  // some column carries LN_EXCL
     int ip = 0, e = 0;                             // e = next equality constraint to add
     double ss = 0.0, s_ip = 0.0;
     bool need_scan = true, l1 = true, done = false;
@@ -355,7 +357,11 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       } else if (need_scan) {
         // ------------------------------------------------ step 1 / 2: scan, choose ip
         if (l1) {
-          excl = ~0ull;
+          if (any_excl) {  // iaexcl[i] = true for all i
+#pragma unroll 1
+            for (int i = 0; i < m; i++) cidx[i] &= (unsigned char)~LN_EXCL;
+            any_excl = false;
+          }
           ss = 0.0;
           ip = 0;
         }
@@ -366,29 +372,27 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           finite = finite && (d_abs(x[j]) < INF);
         }
         double psi = 0.0;
-        unsigned long long elig = ~act & excl;
         bool picked = false;
         if (!has_dense && finite) {
           // every column is (row, value) or empty: s_i = (0.0 + v*x[row]) + ci0_i, bit for bit
 #pragma unroll 6
           for (int i = 0; i < m; i++) {
-            const int c = cidx[i];
-            const double sum = d_add(d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c])), sci0[i]);
+            const unsigned c = cidx[i];
+            const double sum = d_add(d_add(0.0, d_mul(civ[i], sd[c & LN_ROW])), sci0[i]);
             if (sum < 0.0) psi = d_add(psi, sum);  // adding +0.0 otherwise would not change psi
-            if (sum < ss && (elig & 1ull)) {
+            if (sum < ss && c < LN_EXCL) {
               ss = sum;
               ip = i;
               picked = true;
             }
-            elig >>= 1;
           }
         } else {
 #pragma unroll 1
           for (int i = 0; i < m; i++) {
-            const int c = cidx[i];
+            const unsigned c = cidx[i];
             double sum;
-            if (c != LN_DENSE && finite) {
-              sum = d_add(0.0, d_mul(civ[i], sd[c < 0 ? 0 : c]));
+            if (!(c & LN_DENSE) && finite) {
+              sum = d_add(0.0, d_mul(civ[i], sd[c & LN_ROW]));
             } else {
               sum = 0.0;
 #pragma unroll
@@ -396,12 +400,11 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             }
             sum = d_add(sum, sci0[i]);
             psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
-            if (sum < ss && (elig & 1ull)) {
+            if (sum < ss && c < LN_EXCL) {
               ss = sum;
               ip = i;
               picked = true;
             }
-            elig >>= 1;
           }
         }
         if (picked) s_ip = ss;
@@ -423,14 +426,14 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           if (ss >= 0.0) {
             done = true;
           } else {
-            const int c = cidx[ip];
-            if (c == LN_DENSE) {
+            const unsigned c = cidx[ip];
+            if (c & LN_DENSE) {
 #pragma unroll
               for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CI + j * m + ip);
             } else {
               const double a = civ[ip];
 #pragma unroll
-              for (int j = 0; j < N; j++) np[j] = (j == c) ? a : 0.0;
+              for (int j = 0; j < N; j++) np[j] = (j == (int)(c & LN_ROW)) ? a : 0.0;  // a == 0 for an empty column
             }
             su[iq] = 0.0;
             A[iq] = (signed char)ip;
@@ -526,7 +529,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll 1
           for (int k = 0; k < iq; k++) su[k] = d_sub(su[k], d_mul(t, sr[k]));
           su[iq] = d_add(su[iq], t);
-          act &= ~(1ull << l);
+          cidx[l] &= (unsigned char)~LN_ACT;  // iai[l] = l
           do_del = true;
           del_l = l;
         } else {
@@ -539,7 +542,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           if (d_abs(d_sub(t, t2)) < MGQP_EPS) {
             do_add = true;  // full step
           } else {
-            act &= ~(1ull << l);  // partial step: drop l, stay on ip
+            cidx[l] &= (unsigned char)~LN_ACT;  // partial step: drop l (iai[l] = l), stay on ip
             do_del = true;
             del_l = l;
             partial = true;
@@ -583,12 +586,13 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           }
           e++;
         } else if (ok) {
-          act |= 1ull << ip;
+          cidx[ip] |= LN_ACT;  // iai[ip] = -1
           need_scan = true;
           l1 = true;
         } else {
           degenerate = true;
-          excl &= ~(1ull << ip);
+          cidx[ip] |= LN_EXCL;  // iaexcl[ip] = false
+          any_excl = true;
           do_del = true;
           del_l = ip;
         }
@@ -648,13 +652,14 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 
       if (degenerate) {
         // restore the state saved at step 1 and go back to step 2 with the stale ss
-        act = 0ull;
+#pragma unroll 1
+        for (int i = 0; i < m; i++) cidx[i] &= (unsigned char)~LN_ACT;  // iai[i] = i
 #pragma unroll
         for (int i = 0; i <= N; i++)
           if (i >= p && i < iq) {
             A[i] = Aold[i];
             su[i] = uold[i];
-            act |= 1ull << A[i];
+            cidx[A[i]] |= LN_ACT;
           }
 #pragma unroll
         for (int i = 0; i < N; i++) x[i] = xold[i];
