@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -223,7 +224,9 @@ LargePlan make_large_plan(int n, int p, int m, int smem_optin) {
   LargePlan lp;
   int want = n > (m + 3) / 4 ? n : (m + 3) / 4;
   int T = 64;
-  while (T < want && T < 512) T *= 2;
+  int tmax = 256;
+  if (const char* e = std::getenv("MGQP_LARGE_T")) tmax = std::atoi(e);  // tuning knob
+  while (T < want && T < tmax) T *= 2;
   lp.T = T;
   lp.v = make_large_view(n, p, m, T);
   lp.ok = lp.v.smem_bytes + 1024 <= smem_optin && (long long)n * n < (1ll << 30);
@@ -243,7 +246,9 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lp.T, lp.v.smem_bytes));
   if (per_sm < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "CTA-per-QP kernel does not fit an SM (smem %d B)", lp.v.smem_bytes);
-  if (per_sm > 2) per_sm = 2;
+  int cap_sm = 2;
+  if (const char* e = std::getenv("MGQP_LARGE_CTAS_PER_SM")) cap_sm = std::atoi(e);  // tuning knob
+  if (per_sm > cap_sm) per_sm = cap_sm;
   long long ctas = (long long)ctx->sms * per_sm;
   if (ctas > P.batch) ctas = P.batch;
   const long long ws_bytes = lp.v.ws_doubles * 8;
