@@ -165,9 +165,24 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     for (int j = 0; j < n; j++) sR[li * ldR + j] = 0.0;
   }
 
+  // G == I exactly (diagonal 1.0, off-diagonal +0.0, bit for bit) is what the reference's caller
+  // always passes (src/mgqp.cpp:672, :700: JG = Identity).  Then the Cholesky factor is I and
+  // J = L^-T = I with +0.0 zeros, exactly as the general code would produce them (every update is
+  // x - (+0.0 * y) = x and every quotient is x / 1.0), so the factorisation and the n forward
+  // eliminations can be skipped when EVERY QP of the warp has that form.
+  bool row_is_identity = true;
+  if (in_n) {
+    MGQP_UNROLL1
+    for (int j = 0; j < n; j++) {
+      const double gv = sG[li * n + j];
+      row_is_identity = row_is_identity && ((j == li) ? (gv == 1.0) : d_is_pos_zero(gv));
+    }
+  }
+  const bool all_identity = !wp_any(!row_is_identity);
+
   // Cholesky, row-oriented as the reference: lane j owns entry (i, j) of row i
   MGQP_UNROLL1
-  for (int i = 0; i < n; i++) {
+  for (int i = 0; i < (all_identity ? 0 : n); i++) {
     const bool act = in_n && li >= i;
     double sum = 0.0;
     if (act) {
@@ -195,7 +210,10 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   }
 
   // J = L^-T: lane i runs forward_elimination(L, e_i) and keeps the result as row i of J
-  if (in_n) {
+  if (in_n && all_identity) {
+    MGQP_UNROLL1
+    for (int r = 0; r < n; r++) sJ[li * ldJ + r] = (r == li) ? 1.0 : 0.0;
+  } else if (in_n) {
     MGQP_UNROLL1
     for (int r = 0; r < n; r++) {
       double acc = (r == li) ? 1.0 : 0.0;

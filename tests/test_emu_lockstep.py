@@ -74,6 +74,24 @@ def test_degenerate_branch_and_iteration_cap(emu_lib, restatement):
     assert (ref["status"] == 4).any() and (ref["status"] == 0).any()
 
 
+def _identity_mix(B):
+    """As-shipped S0 batch (G = I) with a few QPs whose G is only ALMOST the identity: -0.0 off the
+    diagonal, a diagonal entry one ulp above 1, a genuinely different SPD matrix."""
+    b = workloads.make("S0", B)
+    b.G[3, 2, 5] = -0.0
+    b.G[3, 5, 2] = -0.0
+    b.G[10, 4, 4] = np.nextafter(1.0, 2.0)
+    b.G[17] = workloads.make_random(1, 14, 0, 0, seed=5).G[0]
+    return b
+
+
+def test_identity_fast_path_and_its_fallback(emu_lib, restatement):
+    b = _identity_mix(64)
+    assert_bit_identical(emu_solve(emu_lib, b, 16), _oracle(restatement, b), "S0 identity mix")
+    b = workloads.make("S2", 64)          # every warp all-identity: the fast path itself
+    assert_bit_identical(emu_solve(emu_lib, b, 16), _oracle(restatement, b), "S2")
+
+
 def test_fast_math_mode_within_tolerance(emu_lib, restatement):
     """FMA + tree reductions: not bit-identical by design, but inside the 1e-9 gate."""
     b = workloads.make("C2", 301)

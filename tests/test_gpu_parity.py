@@ -117,6 +117,14 @@ def test_mpc_shape_against_reference_binary_and_oracle(gpu, restatement):
     assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), "C4")
 
 
+def test_identity_g_fast_path_and_its_fallback(gpu, restatement):
+    """G == I exactly (the reference's own caller, src/mgqp.cpp:672) skips the factorisation; a warp
+    that also holds a QP with -0.0 / 1+ulp / a different G must take the general path."""
+    from test_emu_lockstep import _identity_mix
+    for b in (_identity_mix(4099), workloads.make("S2", 4099), workloads.make("S0", 4099)):
+        assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), b.name)
+
+
 def test_empty_batch_and_argument_errors(gpu):
     import torch
     z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device="cuda:0")
