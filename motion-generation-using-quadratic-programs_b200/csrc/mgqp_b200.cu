@@ -169,6 +169,10 @@ LanePlan make_lane_plan(int n, int p, int m, int smem_optin) {
   int warps = (int)((smem_optin - 1024) / per_warp);
   if (warps < 2) return lp;  // one warp per SM cannot hide anything: use the lane-group kernel instead
   if (warps > 8) warps = 8;
+  if (const char* e = std::getenv("MGQP_LANE_WARPS")) {  // tuning knob: fewer resident warps per SM
+    const int w = std::atoi(e);
+    if (w >= 1 && w < warps) warps = w;
+  }
   lp.warps = warps;
   lp.smem = (int)(per_warp * warps);
   lp.ok = true;
