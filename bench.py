@@ -265,8 +265,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                   "f_bit_identical": bool(np.array_equal(fg, chk["f"], equal_nan=True))}
     peak, peak_src = peaks()
     kern_ms = float(np.mean(step_ms))  # one launch per step: the step IS the kernel (+ a 4-byte memset)
-    achieved = B * bytes_per_qp / (kern_ms / 1e3) / 1e9
     gw, warps, smem = mgqp_b200.plan(n, p, m)
+    roof_note = "every input once, x/f/status once (SURVEY.md 8d)"
+    if gw == 0 and not (args.flags & 8):
+        # CTA-per-QP shapes: CI (8*n*m bytes) no longer fits on chip and the algorithm itself reads all of
+        # it in every violated-constraint scan, so that is the algorithmic traffic
+        probe = mgqp_b200.solve_quadprog_batched(*dev_in, flags=args.flags, want_active_set=True)
+        torch.cuda.synchronize()
+        scans = float(probe.iters.double().mean().item()) + 1.0
+        bytes_per_qp = int(bytes_per_qp + (scans - 1.0) * 8 * n * m)
+        roof_note = f"inputs once + CI re-read in each of the {scans:.1f} scans per QP (SURVEY.md 8a a7)"
+    achieved = B * bytes_per_qp / (kern_ms / 1e3) / 1e9
     kname = {1: "gi_lane_kernel<%d> (one QP per lane)" % n, 0: "gi_large_kernel (one QP per CTA)"}.get(
         gw, "gi_small_kernel<%d> (%d lanes per QP)" % (gw, gw))
     if args.flags & 8:
@@ -288,7 +297,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "steps": e2e_steps, "matches_device_leg": e2e_same,
                 "api": "solve_quadprog_batched_host (C ABI, pinned host buffers, chunked 2-stream pipeline)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_qp": bytes_per_qp,
+                     "traffic": None, "peak_source": peak_src, "bytes_per_qp": bytes_per_qp, "bytes_note": roof_note,
                      "kernel_ms": kern_ms},
     }
     if line_cpu:
