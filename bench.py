@@ -300,6 +300,37 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "traffic": None, "peak_source": peak_src, "bytes_per_qp": bytes_per_qp, "bytes_note": roof_note,
                      "kernel_ms": kern_ms},
     }
+    if gw == 0 and not (args.flags & 8):
+        # SURVEY.md 8d for the horizon-stacked shape: the dense factorisation part on its own
+        # (Cholesky n^3/3 + triangular inverse n^3/3 + solve 2n^2 flops), timed by solving the same G, g0
+        # with no constraints, against an fp64 GEMM peak measured here with torch.matmul.
+        z = lambda *sh: torch.zeros(sh, dtype=torch.float64, device=dev)
+        bare = [dev_in[0], dev_in[1], z(B, n, 0), z(B, 0), z(B, n, 0), z(B, 0)]
+        mgqp_b200.solve_quadprog_batched(*bare, flags=args.flags | 16)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            mgqp_b200.solve_quadprog_batched(*bare, flags=args.flags | 16)
+        e1.record()
+        torch.cuda.synchronize()
+        dense_ms = e0.elapsed_time(e1) / 3
+        flops = (2.0 * n ** 3 / 3.0 + 2.0 * n * n) * B
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        torch.matmul(a, a)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            torch.matmul(a, a)
+        e1.record()
+        torch.cuda.synchronize()
+        p64 = 3 * 2.0 * 4096 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
+        line["dense_part"] = {"what": "set-up only (Cholesky, J = L^-T, x0): same G, g0, p = m = 0", "ms": dense_ms,
+                              "tflops": flops / (dense_ms / 1e3) / 1e12, "peak_tflops": p64,
+                              "peak_source": "torch.matmul fp64 4096^3 on this GPU",
+                              "frac": flops / (dense_ms / 1e3) / 1e12 / p64,
+                              "note": "plain FP64 FMA units in reference summation order; no DMMA (it would change "
+                                      "the rounding order of the exact mode)"}
     if line_cpu:
         line["cpu_baseline"] = line_cpu
     if parity:

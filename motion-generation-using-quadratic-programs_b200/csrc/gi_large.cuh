@@ -3,8 +3,9 @@
 //
 // Replaces the body of the reference's solve_quadprog (lib/QuadProgpp/libquadprog.a: QuadProg++.o;
 // prototype include/QuadProgpp/QuadProg++.hh:69-72; spec SURVEY.md Appendix A).  At this size the
-// matrices no longer fit on chip: the Cholesky factor, J and R (n*n doubles each) live in a per-CTA
-// global-memory workspace that stays L2-resident between uses, the vectors and the per-rotation
+// matrices no longer fit on chip: the Cholesky factor, J (stored TRANSPOSED, so that update_z and the
+// Givens sweeps -- thread k works on row k of J -- are coalesced) and R (n*n doubles each) live in a
+// per-CTA global-memory workspace that stays L2-resident between uses, the vectors and the per-rotation
 // Givens coefficients live in shared memory, and CE/CI are read in place (CI once per
 // violated-constraint scan, which is what bounds this kernel: 8*n*m bytes per iteration).
 //
@@ -227,6 +228,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
 
   // Cholesky, row-oriented as the reference; row i is staged in sz for the broadcast operand
   bool fail = false;
+  bool my_nonfinite = false;  // this thread wrote a factor entry that is inf or NaN
   MGQP_UNROLL1
   for (int i = 0; i < n && !fail; i++) {
     MGQP_UNROLL1
@@ -235,9 +237,10 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     MGQP_UNROLL1
     for (int j = i + tid; j < n; j += T) {
       double sum = Gc[(size_t)i * n + j];
-      const double* rowj = Gc + (size_t)j * n;
       MGQP_UNROLL8
-      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sz[k], rowj[k]);
+      // L[j][k] is read as its mirror image Gc[k][j] (written when row k was finished): same bits,
+      // and consecutive threads (j) touch consecutive addresses
+      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sz[k], Gc[(size_t)k * n + j]);
       sd[j] = sum;
     }
     blk_sync();
@@ -252,10 +255,12 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
       for (int j = i + tid; j < n; j += T) {
         if (j == i) {
           Gc[(size_t)i * n + i] = dii;
+          my_nonfinite = my_nonfinite || !(dii < INF);
         } else {
           const double val = d_div(sd[j], dii);
           Gc[(size_t)j * n + i] = val;
           Gc[(size_t)i * n + j] = val;
+          my_nonfinite = my_nonfinite || !(d_abs(val) < INF);
         }
       }
     }
@@ -264,17 +269,31 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
 
   double c2 = 0.0, R_norm = 1.0;
   if (!fail) {
-    // J = L^-T: thread i owns row i = forward_elimination(L, e_i)
+    // J = L^-T: thread i owns row i = forward_elimination(L, e_i).  J is upper triangular: with a
+    // finite factor the entries left of the diagonal are exactly +0.0 and the products they enter
+    // are +-0.0, which never change the accumulator (x - (+-0) = x, and +0.0 - (+-0.0) = +0.0), so the
+    // row can start at its diagonal -- a third of the multiply-adds, bit for bit the same result.  A
+    // factor with inf/NaN in it (a poisoned G) takes the full loops so that the poison spreads
+    // exactly as in the reference.
+    if (tid == 0) sredi[0] = 0;
+    blk_sync();
+    if (my_nonfinite) sredi[0] = 1;
+    blk_sync();
+    const bool finite_L = sredi[0] == 0;
+    blk_sync();
     MGQP_UNROLL1
     for (int i = tid; i < n; i += T) {
-      double* Ji = J + (size_t)i * n;
+      double* Ji = J + i;  // row i of J = column i of the transposed store: element r at Ji[r * n]
+      const int r0 = finite_L ? i : 0;
       MGQP_UNROLL1
-      for (int r = 0; r < n; r++) {
+      for (int r = 0; r < r0; r++) Ji[(size_t)r * n] = 0.0;
+      MGQP_UNROLL1
+      for (int r = r0; r < n; r++) {
         double acc = (r == i) ? 1.0 : 0.0;
         const double* Lr = Gc + (size_t)r * n;
         MGQP_UNROLL8
-        for (int j = 0; j < r; j++) acc = msub<FMA>(acc, Lr[j], Ji[j]);
-        Ji[r] = d_div(acc, Lr[r]);
+        for (int j = r0; j < r; j++) acc = msub<FMA>(acc, Lr[j], Ji[(size_t)j * n]);
+        Ji[(size_t)r * n] = d_div(acc, Lr[r]);
       }
     }
     blk_sync();
@@ -316,16 +335,16 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
       MGQP_UNROLL8
-      for (int j = 0; j < n; j++) s = mad<FMA>(J[(size_t)j * n + i], snp[j], s);
+      for (int j = 0; j < n; j++) s = mad<FMA>(J[(size_t)i * n + j], snp[j], s);  // J[j][i]
       sd[i] = s;
     }
     blk_sync();
     MGQP_UNROLL1
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
-      const double* Ji = J + (size_t)i * n;
+      const double* Ji = J + i;
       MGQP_UNROLL8
-      for (int j = iq; j < n; j++) s = mad<FMA>(Ji[j], sd[j], s);
+      for (int j = iq; j < n; j++) s = mad<FMA>(Ji[(size_t)j * n], sd[j], s);  // J[i][j]
       sz[i] = s;
     }
     blk_sync();
@@ -385,21 +404,21 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     // (3) every thread streams its rows of J right to left through all rotations
     MGQP_UNROLL1
     for (int k = tid; k < n; k += T) {
-      double* Jk = J + (size_t)k * n;
-      double t2 = Jk[n - 1];
+      double* Jk = J + k;  // row k of J, element j at Jk[j * n]: coalesced across the threads
+      double t2 = Jk[(size_t)(n - 1) * n];
       MGQP_UNROLL8
       for (int j = n - 1; j >= iq + 1; j--) {
-        const double t1 = Jk[j - 1];
+        const double t1 = Jk[(size_t)(j - 1) * n];
         if (!skip[j]) {
           const double n1 = d_add(d_mul(t1, scc[j]), d_mul(t2, sss[j]));
-          Jk[j] = d_sub(d_mul(sh[j], d_add(t1, n1)), t2);
+          Jk[(size_t)j * n] = d_sub(d_mul(sh[j], d_add(t1, n1)), t2);
           t2 = n1;
         } else {
-          Jk[j] = t2;
+          Jk[(size_t)j * n] = t2;
           t2 = t1;
         }
       }
-      if (iq + 1 <= n - 1) Jk[iq] = t2;
+      if (iq + 1 <= n - 1) Jk[(size_t)iq * n] = t2;
     }
     // column iq of R <- d[0..iq]
     MGQP_UNROLL1
@@ -485,11 +504,11 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
         }
         MGQP_UNROLL1
         for (int k = tid; k < n; k += T) {
-          double* Jk = J + (size_t)k * n;
-          const double t1 = Jk[j], t2 = Jk[j + 1];
+          double* Jk = J + k;
+          const double t1 = Jk[(size_t)j * n], t2 = Jk[(size_t)(j + 1) * n];
           const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
-          Jk[j] = n1;
-          Jk[j + 1] = d_sub(d_mul(xny, d_add(n1, t1)), t2);
+          Jk[(size_t)j * n] = n1;
+          Jk[(size_t)(j + 1) * n] = d_sub(d_mul(xny, d_add(n1, t1)), t2);
         }
       }
       blk_sync();

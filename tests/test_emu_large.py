@@ -58,3 +58,19 @@ def test_degenerate_and_failures(emu_lib, restatement):
     for k in ("x", "iq", "iters", "A"):
         assert np.array_equal(got[k][keep], ref[k][keep]), k
     assert np.array_equal(got["f"], ref["f"], equal_nan=True)
+
+
+def test_poisoned_factor_takes_the_full_loops(emu_lib, restatement):
+    """inf / NaN inside G: the upper-triangular shortcut of the J computation must not be used, the
+    poison has to spread exactly as in the reference."""
+    b = workloads.make_random(12, 40, 2, 60, seed=77)
+    b.G[1, 3, 4] = b.G[1, 4, 3] = np.inf
+    b.G[2, 5, 5] = np.nan
+    b.G[3, 39, 39] = np.inf
+    ref = _oracle(restatement, b)
+    got = large_solve(emu_lib, b)
+    assert np.array_equal(got["status"], ref["status"])
+    keep = ref["status"] != 2
+    assert np.array_equal(got["x"][keep], ref["x"][keep], equal_nan=True)
+    assert np.array_equal(got["f"], ref["f"], equal_nan=True)
+    assert np.array_equal(got["iters"][keep], ref["iters"][keep])

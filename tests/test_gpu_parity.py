@@ -106,6 +106,19 @@ def test_cta_per_qp_kernel_failures_and_degenerate(gpu, restatement):
     assert np.array_equal(got["f"], ref["f"], equal_nan=True)
 
 
+def test_cta_per_qp_kernel_poisoned_factor(gpu, restatement):
+    b = workloads.make_random(64, 40, 2, 60, seed=77)
+    b.G[1, 3, 4] = b.G[1, 4, 3] = np.inf
+    b.G[2, 5, 5] = np.nan
+    b.G[3, 39, 39] = np.inf
+    ref = _oracle(restatement, b)
+    got = _solve(gpu, b)
+    assert np.array_equal(got["status"], ref["status"])
+    keep = ref["status"] != 2
+    assert np.array_equal(got["x"][keep], ref["x"][keep], equal_nan=True)
+    assert np.array_equal(got["f"], ref["f"], equal_nan=True)
+
+
 def test_mpc_shape_against_reference_binary_and_oracle(gpu, restatement):
     """BASELINE config 4 shape: n = 350, m = 2100.  One QP is pinned by the shipped binary
     (tests/golden/batch_C4_seedonly.npz); a small batch is checked against the oracle."""
