@@ -51,7 +51,7 @@ namespace mgqp {
 
 struct LaneView {
   int n, p, m;
-  int oJ, oR, od, orr, ou, ouold, ociv, oci0, oByte;  // doubles
+  int oR, od, orr, ou, ociv, oci0, oByte;               // doubles
   int bA, bAold, bcidx;                                // bytes, relative to (signed char*)(slot + oByte)
   int stride;                                          // doubles per lane, odd
 };
@@ -65,12 +65,10 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
   LaneView v;
   v.n = n; v.p = p; v.m = m;
   int o = 0;
-  v.oJ = o;     /* J lives in registers */
   v.oR = o;     o += lane_rh_size(n);
   v.od = o;     o += n;
   v.orr = o;    o += n;
   v.ou = o;     o += n + 1;
-  v.ouold = o;  /* u_old lives in registers */
   v.ociv = o;   o += m;
   v.oci0 = o;   o += m;
   // the civ|ci0 area doubles as set-up scratch (L | y | x | g0), the R|d|r|u area as scratch for J

@@ -48,7 +48,9 @@ int fail(int rc, const char* fmt, ...) {
   } while (0)
 
 constexpr int kMaxDev = 16;
-constexpr int kTicketRing = 256;
+// Work-queue heads, one slot per launch, reused round robin: two launches only ever share a slot if
+// more than kTicketRing launches of this library are in flight on one device at the same time.
+constexpr int kTicketRing = 4096;
 
 struct DeviceCtx {
   std::mutex mu;
