@@ -69,7 +69,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libmgqp_b200.so")
+    # MGQP_B200_LIB: developer override used by tools/ab_build.sh to time kernel variants side by side
+    return os.environ.get("MGQP_B200_LIB") or os.path.join(_HERE, "libmgqp_b200.so")
 
 
 def lib():

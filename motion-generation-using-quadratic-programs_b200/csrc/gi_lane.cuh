@@ -47,6 +47,10 @@
 #define MGQP_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
 #endif
 
+#ifndef MGQP_LANE_PQ
+#define MGQP_LANE_PQ 1
+#endif
+
 namespace mgqp {
 
 struct LaneView {
@@ -84,9 +88,10 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
   return v;
 }
 
-// per-column byte: bits 0-2 row of the single nonzero | ONE (a nonzero has been seen) | DENSE (more than
-// one) | EXCL (iaexcl == false) | ACT (iai == -1).  A column may be chosen iff byte < LN_EXCL.
-enum { LN_ROW = 0x07, LN_ONE = 0x10, LN_DENSE = 0x20, LN_EXCL = 0x40, LN_ACT = 0x80 };
+// per-column byte: ONE (a nonzero has been seen) | DENSE (more than one) | bits 3-5 row of the single
+// nonzero, i.e. its byte offset into a vector of doubles | EXCL (iaexcl == false) | ACT (iai == -1).
+// A column may be chosen iff byte < LN_EXCL.
+enum { LN_ONE = 0x01, LN_DENSE = 0x02, LN_ROW = 0x38, LN_ROW_SHIFT = 3, LN_EXCL = 0x40, LN_ACT = 0x80 };
 
 MGQP_DEV double ln_distance(double a, double b) {
   const double a1 = d_abs(a), b1 = d_abs(b);
@@ -126,6 +131,98 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
   return g;
 }
 
+// Stream this lane's CI (N x m, row-major) and ci0 from global memory -- their only read -- and sort the
+// inequality columns into (row, value) form: cidx[i] = flag byte, civ[i] = the single nonzero coefficient
+// (+-0.0 for an empty column), sci0[i] = ci0[i].  Returns true iff some column has more than one nonzero.
+// PQ = 1: with two or three pairs per chunk (or a three-deep ring) ptxas spills the load buffers, and
+// as a separate non-inlined routine the call ABI costs more than it buys (measured, profiles/r01_notes.md).
+template <int N>
+MGQP_DEV bool ln_classify(const double* __restrict__ CI, const double* __restrict__ ci0, int m,
+                                   double* __restrict__ civ, double* __restrict__ sci0, unsigned char* __restrict__ cidx) {
+  bool has_dense = false;
+  const bool vec = ((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(CI) & 15ull) == 0ull) &&
+                   ((reinterpret_cast<unsigned long long>(ci0) & 15ull) == 0ull);
+  if (vec) {
+    // PQ column pairs (one 16-byte load per row of CI, plus one of ci0, per pair) per chunk, the next
+    // chunk's PQ*(N+1) loads in flight while the current one is classified.  Per element: one compare,
+    // one add into the column's running sum and one conditional integer add into its (count, row)
+    // word -- with at most one nonzero in a column the sum IS that coefficient bit for bit
+    // (v + (+-0.0) == v), and count*64 + 8*row is the flag byte.
+    constexpr int PQ = MGQP_LANE_PQ;
+    const int mh = m >> 1;
+    double bufA[PQ][N + 1][2], bufB[PQ][N + 1][2];
+    auto load_chunk = [&](double (&b)[PQ][N + 1][2], int c) {
+#pragma unroll
+      for (int q = 0; q < PQ; q++)
+        if (c + q < mh) {
+#pragma unroll
+          for (int j = 0; j < N; j++) MGQP_LDG2(CI + j * m + 2 * (c + q), b[q][j][0], b[q][j][1]);
+          MGQP_LDG2(ci0 + 2 * (c + q), b[q][N][0], b[q][N][1]);
+        }
+    };
+    auto sort_chunk = [&](const double (&b)[PQ][N + 1][2], int c) {
+#pragma unroll
+      for (int q = 0; q < PQ; q++)
+        if (c + q < mh) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            double val = b[q][0][h];
+            unsigned acc = (b[q][0][h] != 0.0) ? 64u : 0u;  // NaN counts as nonzero
+#pragma unroll
+            for (int j = 1; j < N; j++) {
+              val = d_add(val, b[q][j][h]);
+              if (b[q][j][h] != 0.0) acc += 64u + 8u * j;
+            }
+            const int i = 2 * (c + q) + h;
+            unsigned byte = (acc & LN_ROW) | LN_ONE;
+            if (acc < 64u) byte = 0;
+            if (acc >= 128u) {
+              byte = LN_ONE | LN_DENSE;
+              has_dense = true;
+            }
+            cidx[i] = (unsigned char)byte;
+            civ[i] = val;
+            sci0[i] = b[q][N][h];
+          }
+        }
+    };
+    load_chunk(bufA, 0);
+#pragma unroll 1
+    for (int c = 0; c < mh; c += 2 * PQ) {
+      load_chunk(bufB, c + PQ);
+      sort_chunk(bufA, c);
+      load_chunk(bufA, c + 2 * PQ);
+      sort_chunk(bufB, c + PQ);
+    }
+  } else {
+    // odd m or unaligned fields: element-wise row sweep
+#pragma unroll 1
+    for (int i = 0; i < m; i++) {
+      cidx[i] = 0;
+      civ[i] = 0.0;
+      sci0[i] = MGQP_LDG(ci0 + i);
+    }
+#pragma unroll 1
+    for (int j = 0; j < N; j++) {
+      const double* row = CI + j * m;
+#pragma unroll 4
+      for (int i = 0; i < m; i++) {
+        const double a = MGQP_LDG(row + i);
+        if (a != 0.0) {  // NaN counts as nonzero
+          if (!(cidx[i] & LN_ONE)) {
+            cidx[i] = (unsigned char)((j << LN_ROW_SHIFT) | LN_ONE);
+            civ[i] = a;
+          } else {
+            cidx[i] |= LN_DENSE;
+            has_dense = true;
+          }
+        }
+      }
+    }
+  }
+  return has_dense;
+}
+
 struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
 };
@@ -149,9 +246,9 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
   int status = 0, iq = 0, steps = 0;
   double f = 0.0;
   bool has_dense = false;  // some inequality column has more than one nonzero
-  double x[N], z[N], np[N], dd[N], xold[N];
+  double x[N];
 #pragma unroll
-  for (int i = 0; i < N; i++) { x[i] = 0.0; z[i] = 0.0; np[i] = 0.0; dd[i] = 0.0; xold[i] = 0.0; }
+  for (int i = 0; i < N; i++) x[i] = 0.0;
 
   // ---------------------------------------------------------------- set-up
   // Cholesky of G, J = L^-T and x0 = -G^-1 g0 run out of shared-memory scratch that the constraint
@@ -183,6 +280,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
   for (int i = 0; i < N; i++) c1 = d_add(c1, Ls[i * N + i]);
 
   bool fail = false;
+  bool lfin = true;  // every off-diagonal entry of the Cholesky factor is finite
   double bad_pivot = 0.0;
 #pragma unroll 1
   for (int i = 0; i < N && !fail; i++) {
@@ -206,12 +304,14 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     } else {
       const double dii = d_sqrt(piv);
       Ls[i * N + i] = dii;
+      lfin = lfin && (dii < INF);
 #pragma unroll
       for (int j = 0; j < N; j++)
         if (j > i) {
           const double val = d_div(sum[j], dii);
           Ls[j * N + i] = val;
           Ls[i * N + j] = val;
+          lfin = lfin && (d_abs(val) < INF);
         }
     }
   }
@@ -233,9 +333,14 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll
         for (int i = 0; i < N; i++) acc[i] = msub<FMA>(acc[i], lrj, Js[i * N + j]);
       }
+      // Row i of J solves L z = e_i, so z_r = +0.0 for r < i whenever the factor is finite
+      // (0.0 - l*0.0 = +0.0, +0.0 / l_rr = +0.0): those 21 divisions are skipped.
       const double lrr = Ls[r * N + r];
 #pragma unroll
-      for (int i = 0; i < N; i++) Js[i * N + r] = d_div(acc[i], lrr);
+      for (int i = 0; i < N; i++) {
+        if (i <= r || !lfin) Js[i * N + r] = d_div(acc[i], lrr);
+        else Js[i * N + r] = 0.0;
+      }
     }
 #pragma unroll
     for (int i = 0; i < N; i++) c2 = d_add(c2, Js[i * N + i]);
@@ -263,72 +368,20 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
       fs = mad<FMA>(g0s[i], x[i], fs);
     }
     f = d_mul(0.5, fs);
-    // J moves into REGISTERS for the whole solve: every access below has compile-time indices (the
-    // Givens sweeps are unrolled over the column index and predicated on the lane's own iq), which
-    // keeps J out of shared memory (6 resident warps per SM instead of 4) and removes ~100
+    // ---------------------------------------------------------------- inequality columns: classify
+    // (after the set-up, whose L | y | x | g0 scratch it overwrites; J waits in its own scratch so that
+    // the registers are free for the load pipeline)
+    if (m > 0) has_dense = ln_classify<N>(io.CI, io.ci0, m, civ, sci0, cidx);
+
+    // J moves into REGISTERS for the rest of the solve: every access below has compile-time indices
+    // (the Givens sweeps are unrolled over the column index and predicated on the lane's own iq),
+    // which keeps J out of shared memory (6 resident warps per SM instead of 4) and removes ~100
     // shared-memory loads from every iteration.
     double Jr[N][N];
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll
       for (int j = 0; j < N; j++) Jr[i][j] = Js[i * N + j];
-
-    // ---------------------------------------------------------------- inequality columns: classify
-    // (after the set-up: it overwrites the scratch)
-  // Row-major sweep of this QP's CI straight from global memory (each 32-byte sector is fetched from
-  // HBM once and then served by L1 for the lane's next loads); ci0 is parked in the slot.
-    {
-#pragma unroll 1
-    for (int i = 0; i < m; i++) {
-      cidx[i] = 0;
-      civ[i] = 0.0;
-    }
-    auto classify = [&](double a, int j, int i) {
-      if (a != 0.0) {  // NaN counts as nonzero
-        if (!(cidx[i] & LN_ONE)) {
-          cidx[i] = (unsigned char)(j | LN_ONE);
-          civ[i] = a;
-        } else {
-          cidx[i] |= LN_DENSE;
-          has_dense = true;
-        }
-      }
-    };
-    const int nm = N * m;
-    if (((nm & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.CI) & 15ull) == 0ull)) {
-      // 16-byte loads, 6 in flight per lane: a 32-byte sector is consumed by two back-to-back loads of the
-      // same lane instead of living in L1 across loop iterations
-      int j = 0, i = 0;
-#pragma unroll 6
-      for (int e = 0; e < nm; e += 2) {
-        double a0, a1;
-        MGQP_LDG2(io.CI + e, a0, a1);
-        classify(a0, j, i);
-        if (++i == m) { i = 0; j++; }
-        classify(a1, j, i);
-        if (++i == m) { i = 0; j++; }
-      }
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < N; j++) {
-        const double* row = io.CI + j * m;
-#pragma unroll 6
-        for (int i = 0; i < m; i++) classify(MGQP_LDG(row + i), j, i);
-      }
-    }
-    if (((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(io.ci0) & 15ull) == 0ull)) {
-#pragma unroll 4
-      for (int i = 0; i < m; i += 2) {
-        double a0, a1;
-        MGQP_LDG2(io.ci0 + i, a0, a1);
-        sci0[i] = a0;
-        sci0[i + 1] = a1;
-      }
-    } else {
-#pragma unroll 6
-      for (int i = 0; i < m; i++) sci0[i] = MGQP_LDG(io.ci0 + i);
-    }
-  }
 
 #pragma unroll 1
     for (int i = 0; i < lane_rh_size(N); i++) R[i] = 0.0;
@@ -339,7 +392,16 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     int ip = 0, e = 0;                             // e = next equality constraint to add
     double ss = 0.0, s_ip = 0.0;
     bool need_scan = true, l1 = true, done = false;
-    double uold[N + 1];
+    double z[N], np[N], dd[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { z[i] = 0.0; np[i] = 0.0; dd[i] = 0.0; }
+    // The step-1 snapshot (x_old, u_old) is written every outer iteration but read back only on the
+    // rare degenerate branch: it lives in thread-local memory on purpose (volatile keeps it there).
+    // Stores do not stall, and the 30 registers it would take otherwise made the compiler spill
+    // loop scalars whose reloads -- L1 is tiny next to 224 KB of shared memory -- cost an L2 round trip.
+    volatile double xold[N], uold[N + 1];
+#pragma unroll
+    for (int i = 0; i < N; i++) xold[i] = 0.0;
 #pragma unroll
     for (int i = 0; i <= N; i++) uold[i] = 0.0;
 
@@ -370,18 +432,18 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
           finite = finite && (d_abs(x[j]) < INF);
         }
         double psi = 0.0;
-        bool picked = false;
+        const double ss_in = ss;
         if (!has_dense && finite) {
-          // every column is (row, value) or empty: s_i = (0.0 + v*x[row]) + ci0_i, bit for bit
+          // every column is (row, value) or empty: s_i = v*x[row] + ci0_i equals the reference's N-term
+          // sum wherever a comparison can see it (the two can differ in the sign of a zero only)
 #pragma unroll 6
           for (int i = 0; i < m; i++) {
             const unsigned c = cidx[i];
-            const double sum = d_add(d_add(0.0, d_mul(civ[i], sd[c & LN_ROW])), sci0[i]);
-            if (sum < 0.0) psi = d_add(psi, sum);  // adding +0.0 otherwise would not change psi
+            const double sum = d_add(d_mul(civ[i], sd[(c & LN_ROW) >> LN_ROW_SHIFT]), sci0[i]);
+            d_acc_neg(psi, sum);  // psi += min(0, sum); a NaN sum adds nothing, as in the reference
             if (sum < ss && c < LN_EXCL) {
               ss = sum;
               ip = i;
-              picked = true;
             }
           }
         } else {
@@ -390,21 +452,21 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             const unsigned c = cidx[i];
             double sum;
             if (!(c & LN_DENSE) && finite) {
-              sum = d_add(0.0, d_mul(civ[i], sd[c & LN_ROW]));
+              sum = d_mul(civ[i], sd[(c & LN_ROW) >> LN_ROW_SHIFT]);
             } else {
               sum = 0.0;
 #pragma unroll
               for (int j = 0; j < N; j++) sum = mad<FMA>(MGQP_LDG(io.CI + j * m + i), x[j], sum);
             }
             sum = d_add(sum, sci0[i]);
-            psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
+            d_acc_neg(psi, sum);
             if (sum < ss && c < LN_EXCL) {
               ss = sum;
               ip = i;
-              picked = true;
             }
           }
         }
+        const bool picked = ss < ss_in;  // ss only ever moves down, strictly
         if (picked) s_ip = ss;
         if (l1) {
           if (d_abs(psi) <= thr) {
@@ -431,7 +493,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             } else {
               const double a = civ[ip];
 #pragma unroll
-              for (int j = 0; j < N; j++) np[j] = (j == (int)(c & LN_ROW)) ? a : 0.0;  // a == 0 for an empty column
+              for (int j = 0; j < N; j++) np[j] = (j == (int)((c & LN_ROW) >> LN_ROW_SHIFT)) ? a : 0.0;  // a == +-0 for an empty column
             }
             su[iq] = 0.0;
             A[iq] = (signed char)ip;
@@ -458,12 +520,13 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
         sd[i] = s;
       }
 #pragma unroll
-      for (int i = 0; i < N; i++) {
-        double s = 0.0;
+      for (int i = 0; i < N; i++) z[i] = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; j++)
-          if (j >= iq) s = mad<FMA>(Jr[i][j], dd[j], s);
-        z[i] = s;
+      for (int j = 0; j < N; j++) {
+        if (j >= iq) {  // a branch, not a select: columns below the warp's smallest iq cost nothing
+#pragma unroll
+          for (int i = 0; i < N; i++) z[i] = mad<FMA>(Jr[i][j], dd[j], z[i]);
+        }
       }
 #pragma unroll 1
       for (int i = iq - 1; i >= 0; i--) {

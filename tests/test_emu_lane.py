@@ -73,3 +73,18 @@ def test_non_finite_inputs(emu_lib, restatement):
     got = lane_solve(emu_lib, b)
     assert np.array_equal(got["status"], ref["status"])
     assert np.array_equal(got["x"], ref["x"], equal_nan=True) and np.array_equal(got["f"], ref["f"], equal_nan=True)
+
+
+def test_non_finite_cholesky_factor(emu_lib, restatement):
+    """The structural zeros of J = L^-T are only skipped while the factor is finite."""
+    b = workloads.make("C2", 2048)
+    b.G[3::89, 1, 4] = np.inf      # read (upper triangle): an infinite off-diagonal factor entry
+    b.G[5::97, 0, 6] = np.nan
+    b.G[7::101, 6, 6] = np.nan     # NaN pivot passes the `sum <= 0` test of the reference
+    b.G[11::103, 2, 2] = np.inf
+    b.G[13::107, 0, 3] = 1e200     # overflows further down the factorisation
+    ref = _oracle(restatement, b)
+    got = lane_solve(emu_lib, b)
+    assert np.array_equal(got["status"], ref["status"])
+    assert np.array_equal(got["x"], ref["x"], equal_nan=True) and np.array_equal(got["f"], ref["f"], equal_nan=True)
+    assert np.array_equal(got["iters"], ref["iters"])
