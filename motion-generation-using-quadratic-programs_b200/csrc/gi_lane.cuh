@@ -40,11 +40,15 @@
 #ifdef MGQP_EMULATE
 #define MGQP_LDG(p) (*(p))
 #define MGQP_LDG2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
+#define MGQP_LDG2_STREAM(p, a, b) MGQP_LDG2(p, a, b)
 #define MGQP_PREFETCH_L2(p) do { } while (0)
 #else
 #define MGQP_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define MGQP_LDG(p) __ldg(p)
 #define MGQP_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
+// streaming 16-byte load that is cached in L2 only: each lane touches its own 128-byte lines, and the
+// few KB of L1 left beside 224 KB of shared memory cannot hold them until their other sectors are read
+#define MGQP_LDG2_STREAM(p, a, b) asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p))
 #endif
 
 #ifndef MGQP_LANE_PQ
@@ -156,8 +160,8 @@ MGQP_DEV bool ln_classify(const double* __restrict__ CI, const double* __restric
       for (int q = 0; q < PQ; q++)
         if (c + q < mh) {
 #pragma unroll
-          for (int j = 0; j < N; j++) MGQP_LDG2(CI + j * m + 2 * (c + q), b[q][j][0], b[q][j][1]);
-          MGQP_LDG2(ci0 + 2 * (c + q), b[q][N][0], b[q][N][1]);
+          for (int j = 0; j < N; j++) MGQP_LDG2_STREAM(CI + j * m + 2 * (c + q), b[q][j][0], b[q][j][1]);
+          MGQP_LDG2_STREAM(ci0 + 2 * (c + q), b[q][N][0], b[q][N][1]);
         }
     };
     auto sort_chunk = [&](const double (&b)[PQ][N + 1][2], int c) {
@@ -186,6 +190,9 @@ MGQP_DEV bool ln_classify(const double* __restrict__ CI, const double* __restric
           }
         }
     };
+    // (All of these loads share one hardware scoreboard -- ptxas' choice -- so the first use of a buffer
+    // also waits for the loads issued after it: each trip of this loop exposes one full round trip to L2
+    // whatever the order of its four stages.  Ordering fences and a three-deep ring were measured: no gain.)
     load_chunk(bufA, 0);
 #pragma unroll 1
     for (int c = 0; c < mh; c += 2 * PQ) {
@@ -271,6 +278,8 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
   double* xs = ys + N;
   double* g0s = xs + N;
   double* Js = S + v.oR;
+  // (element-wise on purpose: 16-byte loads at each lane's own parity halve the requests but measured
+  // 4 % slower -- these loads hit L1 for the rest of each sector and are issued long before their use)
 #pragma unroll
   for (int i = 0; i < N * N; i++) Ls[i] = MGQP_LDG(io.G + i);
 #pragma unroll
