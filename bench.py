@@ -238,8 +238,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(t.item())
-    h2d = sum(a.nbytes for a in host_np)
-    d2h = res.x.nbytes + res.f.nbytes + res.status.nbytes
+    # bytes that actually crossed the link in the last call (the library counts its own copies): where a
+    # chunk's CI is a set of bounds it travels column-compressed (m*9 bytes, mgqp_batch::CI_val) instead
+    # of as the dense n*m*8-byte block the caller handed over
+    h2d, d2h = mgqp_b200.last_transfer_bytes()
+    host_bytes = sum(a.nbytes for a in host_np)
     e2e_same = bool(np.array_equal(res.status, status) and np.array_equal(res.x, out.x.cpu().numpy()))
 
     if rank != 0:
@@ -294,8 +297,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "matches_device_leg": e2e_same,
-                "api": "solve_quadprog_batched_host (C ABI, pinned host buffers, chunked 2-stream pipeline)"},
+                "steps": e2e_steps, "matches_device_leg": e2e_same, "host_input_bytes_per_step": int(host_bytes),
+                "api": "solve_quadprog_batched_host (C ABI, pinned host buffers, chunked 2-stream pipeline; CI is "
+                       "packed on the host cores into (row, value) columns when every column is a bound"
+                       + (" -- disabled by --flags 32)" if args.flags & 32 else ")")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "bytes_per_qp": bytes_per_qp, "bytes_note": roof_note,
                      "kernel_ms": kern_ms},

@@ -67,7 +67,10 @@ enum {
    * kernel (n <= 8, m <= 64) would be picked. */
   MGQP_FLAG_GROUP_KERNEL = 8,
   /* Always use the CTA-per-QP kernel (the one that serves n > 32). */
-  MGQP_FLAG_CTA_KERNEL = 16
+  MGQP_FLAG_CTA_KERNEL = 16,
+  /* Host-buffer entry points only: ship CI to the device as it is (dense) instead of in the
+   * column-compressed transport form described at mgqp_batch::CI_val. */
+  MGQP_FLAG_NO_HOST_PACK = 32
 };
 
 /* One batch of `batch` independent QPs of one shape, field-wise SoA, DEVICE pointers.
@@ -89,6 +92,18 @@ typedef struct mgqp_batch {
   int32_t* iters;  /* [batch]    number of step-direction computations (l2a passes); or NULL  */
   int32_t max_iter; /* <= 0: default 100 + 10*(p+m)                                            */
   int32_t flags;    /* MGQP_FLAG_*                                                              */
+  /* Optional COLUMN-COMPRESSED form of CI, for batches in which every inequality has at most one
+   * nonzero coefficient -- a bound on one variable, which is every inequality the reference itself
+   * builds (limitsMatrix = [-I; +I], src/mgqp.cpp:1080-1128).  When CI_val != NULL, CI / sCI are
+   * ignored and column i of QP b is  CI_val[b*sCIv + i] * e_k  with  k = CI_row[b*sCIr + i] < n
+   * (an all-zero column: value 0, any row).  m*9 bytes per QP instead of n*m*8.  Served by the
+   * one-QP-per-lane kernel (n <= 8, m <= 64); other shapes return MGQP_ERR_UNSUPPORTED_SHAPE.
+   * The host-buffer entry points build this form themselves, chunk by chunk, on host threads
+   * (mgqp_pack_bound_columns) whenever a chunk qualifies, so that the PCIe link carries 1.2 KB
+   * instead of 3.2 KB per 7-DoF QP; results are bit-identical either way. */
+  const double* CI_val;
+  const uint8_t* CI_row;
+  int64_t sCIv, sCIr; /* element strides between QPs (>= m); 0 broadcasts */
 } mgqp_batch;
 
 /* Solve a device-resident batch on `device`, asynchronously on `stream` (a cudaStream_t passed
@@ -113,6 +128,16 @@ int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int nd
 int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const double* g0,
                    const double* CE, const double* ce0, const double* CI, const double* ci0,
                    double* x, double* f, int32_t* status, double* G_factor, int device);
+
+/* Column-compress the CI blocks of `count` QPs (host memory, QuadProg++ layout n*m, element stride
+ * sCI between QPs) into val[count][sv] / row[count][sr] as described at mgqp_batch::CI_val.
+ * Returns 1 if every column of every QP has at most one nonzero coefficient (the output is then
+ * valid), 0 otherwise.  Pure host code, re-entrant; `threads` <= 0 picks the host's core count. */
+int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI,
+                            double* val, int64_t sv, uint8_t* row, int64_t sr, int threads);
+
+/* Bytes the last host-buffer call of the calling thread moved over the host<->device link. */
+void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h);
 
 /* Introspection. */
 const char* mgqp_status_string(int status);

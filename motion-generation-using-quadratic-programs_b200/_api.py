@@ -27,7 +27,8 @@ import numpy as np
 __all__ = [
     "LogicError", "QPResult", "STATUS", "lib", "lib_path", "solve_quadprog", "solve_quadprog_batched",
     "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
-    "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL", "mgqp_batch",
+    "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL",
+    "FLAG_NO_HOST_PACK", "mgqp_batch", "pack_bound_columns", "last_transfer_bytes",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,6 +37,7 @@ FLAG_NO_BULK_COPY = 2
 FLAG_STATIC_SCHEDULE = 4
 FLAG_GROUP_KERNEL = 8
 FLAG_CTA_KERNEL = 16
+FLAG_NO_HOST_PACK = 32
 STATUS = {0: "ok", 1: "infeasible", 2: "not_pd", 3: "eq_dependent", 4: "iter_cap"}
 
 
@@ -53,6 +55,7 @@ class mgqp_batch(C.Structure):
         ("x", C.c_void_p), ("f", C.c_void_p), ("status", C.c_void_p), ("iq", C.c_void_p),
         ("A", C.c_void_p), ("iters", C.c_void_p),
         ("max_iter", C.c_int32), ("flags", C.c_int32),
+        ("CI_val", C.c_void_p), ("CI_row", C.c_void_p), ("sCIv", C.c_int64), ("sCIr", C.c_int64),
     ]
 
 
@@ -101,6 +104,11 @@ def lib():
         L.mgqp_plan.argtypes = [C.c_int32] * 3 + [C.POINTER(C.c_int32)] * 2
         L.mgqp_algorithmic_bytes.restype = C.c_int64
         L.mgqp_algorithmic_bytes.argtypes = [C.c_int32] * 3
+        L.mgqp_pack_bound_columns.restype = C.c_int
+        L.mgqp_pack_bound_columns.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.c_void_p, C.c_int64, C.c_int]
+        L.mgqp_last_transfer_bytes.restype = None
+        L.mgqp_last_transfer_bytes.argtypes = [C.POINTER(C.c_int64)] * 2
         _lib = L
     return _lib
 
@@ -130,14 +138,36 @@ def kernel_launch_count() -> int:
     return int(lib().mgqp_kernel_launch_count())
 
 
+def last_transfer_bytes():
+    """(host->device, device->host) bytes moved by this thread's last host-buffer call."""
+    up, down = C.c_int64(0), C.c_int64(0)
+    lib().mgqp_last_transfer_bytes(C.byref(up), C.byref(down))
+    return up.value, down.value
+
+
+def pack_bound_columns(CI, threads: int = 0):
+    """Column-compress ``CI [B,n,m]`` (host array): returns ``(val [B,m] float64, row [B,m] uint8)`` or
+    ``None`` if some column has more than one nonzero coefficient (mgqp_batch::CI_val in the header)."""
+    CI = np.ascontiguousarray(CI, dtype=np.float64)
+    B, n, m = CI.shape
+    val = np.empty((B, m))
+    row = np.empty((B, m), dtype=np.uint8)
+    ok = lib().mgqp_pack_bound_columns(n, m, B, CI.ctypes.data, n * m, val.ctypes.data, m, row.ctypes.data, m, threads)
+    return (val, row) if ok else None
+
+
 # ------------------------------------------------------------------ device-resident batches
 def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = False, max_iter: int = 0,
-                           flags: int = 0, stream=None, out: Optional[QPResult] = None) -> QPResult:
+                           flags: int = 0, stream=None, out: Optional[QPResult] = None,
+                           CI_val=None, CI_row=None) -> QPResult:
     """Solve a batch of QPs held in CUDA tensors (float64).
 
     Shapes: ``G [B,n,n]``, ``g0 [B,n]``, ``CE [B,n,p]``, ``ce0 [B,p]``, ``CI [B,n,m]``, ``ci0 [B,m]``;
     a leading dimension of 1 broadcasts that field to the whole batch.  Asynchronous on ``stream``
     (default: torch's current stream).  Returns torch tensors on the same device.
+
+    ``CI_val [B,m]`` (float64) / ``CI_row [B,m]`` (uint8), if given, replace ``CI`` by its
+    column-compressed form (every inequality a bound on one variable; ``CI`` may then be ``None``).
     """
     import torch
 
@@ -147,6 +177,14 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
     n = G.shape[-1]
     p = ce0.shape[-1]
     m = ci0.shape[-1]
+    if CI_val is not None:
+        if CI_row is None or CI_val.dtype != torch.float64 or CI_row.dtype != torch.uint8:
+            raise ValueError("CI_val (float64) and CI_row (uint8) go together")
+        if tuple(CI_val.shape[1:]) != (m,) or tuple(CI_row.shape[1:]) != (m,):
+            raise LogicError(f"The compressed CI is incompatible (expecting [B, {m}])")
+        CI_val, CI_row = CI_val.contiguous(), CI_row.contiguous()
+        if CI is None:
+            CI = torch.empty((1, n, m), dtype=torch.float64, device=dev)  # never read
     B = max(t.shape[0] for t in (G, g0, CE, ce0, CI, ci0))
     _validate_shapes(n, p, m, tuple(G.shape[1:]), tuple(g0.shape[1:]), tuple(CE.shape[1:]), tuple(ce0.shape[1:]),
                      tuple(CI.shape[1:]), tuple(ci0.shape[1:]))
@@ -183,6 +221,10 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
     d.A = out.A.data_ptr() if out.A is not None else None
     d.iters = out.iters.data_ptr() if out.iters is not None else None
     d.max_iter, d.flags = max_iter, flags
+    if CI_val is not None and m:
+        d.CI_val, d.CI_row = CI_val.data_ptr(), CI_row.data_ptr()
+        d.sCIv = 0 if CI_val.shape[0] == 1 and B > 1 else m
+        d.sCIr = 0 if CI_row.shape[0] == 1 and B > 1 else m
     if stream is None:
         stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)

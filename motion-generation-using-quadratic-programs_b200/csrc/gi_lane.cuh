@@ -232,7 +232,43 @@ MGQP_DEV bool ln_classify(const double* __restrict__ CI, const double* __restric
 
 struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
+  // lane kernel only: column-compressed CI (mgqp_batch::CI_val / CI_row); CI is unused when CIv is set
+  const double* CIv = nullptr;
+  const unsigned char* CIr = nullptr;
 };
+
+// Column-compressed constraints as they come from the caller (or from the host pipeline's packer): the
+// (row, value) form the classification would have produced, taken as is.  A row index >= N cannot come
+// from a well-formed batch; it is clamped so that a corrupt one stays inside the lane's slot.
+template <int N>
+MGQP_DEV void ln_take_compressed(const double* __restrict__ CIv, const unsigned char* __restrict__ CIr,
+                                 const double* __restrict__ ci0, int m, double* __restrict__ civ,
+                                 double* __restrict__ sci0, unsigned char* __restrict__ cidx) {
+  const bool vec = ((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(CIv) & 15ull) == 0ull) &&
+                   ((reinterpret_cast<unsigned long long>(ci0) & 15ull) == 0ull);
+  if (vec) {
+#pragma unroll 7
+    for (int i = 0; i < m; i += 2) {
+      double a0, a1, b0, b1;
+      MGQP_LDG2(CIv + i, a0, a1);
+      MGQP_LDG2(ci0 + i, b0, b1);
+      civ[i] = a0; civ[i + 1] = a1;
+      sci0[i] = b0; sci0[i + 1] = b1;
+    }
+  } else {
+#pragma unroll 4
+    for (int i = 0; i < m; i++) {
+      civ[i] = MGQP_LDG(CIv + i);
+      sci0[i] = MGQP_LDG(ci0 + i);
+    }
+  }
+#pragma unroll 4
+  for (int i = 0; i < m; i++) {
+    unsigned r = MGQP_LDG(CIr + i);
+    r = r < (unsigned)N ? r : (unsigned)(N - 1);
+    cidx[i] = (unsigned char)((r << LN_ROW_SHIFT) | LN_ONE);
+  }
+}
 
 template <int N, bool FMA>
 MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int max_iter, double* x_out,
@@ -265,8 +301,8 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
   // Pull this lane's constraint data towards L2 now; it is consumed right after the set-up (a
   // whole-tile-ahead prefetch was evicted before use and doubled the DRAM traffic, this one is not).
   {
-    const char* pc = reinterpret_cast<const char*>(io.CI);
-    const int bytes = N * m * 8;
+    const char* pc = reinterpret_cast<const char*>(io.CIv ? io.CIv : io.CI);
+    const int bytes = (io.CIv ? 1 : N) * m * 8;
 #pragma unroll 4
     for (int o = 0; o < bytes; o += 128) MGQP_PREFETCH_L2(pc + o);
     const char* p0 = reinterpret_cast<const char*>(io.ci0);
@@ -380,7 +416,10 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     // ---------------------------------------------------------------- inequality columns: classify
     // (after the set-up, whose L | y | x | g0 scratch it overwrites; J waits in its own scratch so that
     // the registers are free for the load pipeline)
-    if (m > 0) has_dense = ln_classify<N>(io.CI, io.ci0, m, civ, sci0, cidx);
+    if (m > 0) {
+      if (io.CIv) ln_take_compressed<N>(io.CIv, io.CIr, io.ci0, m, civ, sci0, cidx);
+      else has_dense = ln_classify<N>(io.CI, io.ci0, m, civ, sci0, cidx);
+    }
 
     // J moves into REGISTERS for the rest of the solve: every access below has compile-time indices
     // (the Givens sweeps are unrolled over the column index and predicated on the lane's own iq),
@@ -462,6 +501,14 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             double sum;
             if (!(c & LN_DENSE) && finite) {
               sum = d_mul(civ[i], sd[(c & LN_ROW) >> LN_ROW_SHIFT]);
+            } else if (!(c & LN_DENSE)) {
+              // non-finite x: the reference's full sum, with the column rebuilt from its (row, value)
+              // form -- a zero coefficient times a non-finite x[j] is a NaN term there, too
+              sum = 0.0;
+              const int k = (int)((c & LN_ROW) >> LN_ROW_SHIFT);
+              const double a = civ[i];
+#pragma unroll
+              for (int j = 0; j < N; j++) sum = mad<FMA>((j == k) ? a : 0.0, x[j], sum);
             } else {
               sum = 0.0;
 #pragma unroll

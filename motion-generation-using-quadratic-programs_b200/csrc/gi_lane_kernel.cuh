@@ -17,6 +17,9 @@ struct LaneParams {
   long long batch, tiles;
   const double* in[6];   // G, g0, CE, ce0, CI, ci0
   long long stride[6];
+  const double* ci_val;  // column-compressed CI (mgqp_batch::CI_val / CI_row) or null
+  const unsigned char* ci_row;
+  long long s_ci_val, s_ci_row;
   double* x; double* f; int* status; int* iq; int* A; int* iters;
   int max_iter;
   unsigned* ticket;
@@ -57,6 +60,10 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
     io.ce0 = P.in[3] + myq * P.stride[3];
     io.CI = P.in[4] + myq * P.stride[4];
     io.ci0 = P.in[5] + myq * P.stride[5];
+    if (P.ci_val) {
+      io.CIv = P.ci_val + myq * P.s_ci_val;
+      io.CIr = P.ci_row + myq * P.s_ci_row;
+    }
     double xo[N];
     double f;
     int status, iq, iters;

@@ -1,0 +1,218 @@
+// Host side of the column-compressed constraint transport (mgqp_batch::CI_val / CI_row in
+// include/mgqp_b200.h): turns the dense n x m inequality block the reference's caller builds
+// (src/mgqp.cpp:1080-1128: limitsMatrix = [-I; +I], one nonzero per column) into m (value, row)
+// pairs per QP, so that the PCIe link carries m*9 instead of n*m*8 bytes.  This is a transport
+// codec, not a solver: no arithmetic of the QP is done here, and a chunk in which any column has a
+// second nonzero is shipped dense instead.
+//
+// Plain C++ compiled by the host compiler (not nvcc's front end): the inner loop has an AVX2 version
+// picked at run time.
+#include <stdint.h>
+#include <string.h>
+
+#include <sched.h>
+#include <stdlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/mgqp_b200.h"
+
+namespace {
+
+// One QP (m <= 64 here; the lane kernel's limit).  Each row of CI becomes a bit mask of its nonzero
+// entries (+-0.0 are the zeros, NaN counts as nonzero); a column with two nonzeros shows up as a bit
+// common to two rows.  The ~m nonzeros are then scattered into (val, row); an all-zero column gets
+// (+0.0, row 0).  Returns 1 if some column has more than one nonzero.
+inline int scatter_row(uint64_t mask, int j, const double* r, double* val, uint8_t* row) {
+  while (mask) {
+    const int i = __builtin_ctzll(mask);
+    mask &= mask - 1;
+    val[i] = r[i];
+    row[i] = (uint8_t)j;
+  }
+  return 0;
+}
+
+int pack_one_generic(int n, int m, const double* __restrict__ ci, double* __restrict__ val, uint8_t* __restrict__ row) {
+  for (int i = 0; i < m; i++) {
+    val[i] = 0.0;
+    row[i] = 0;
+  }
+  uint64_t seen = 0, dup = 0;
+  for (int j = 0; j < n; j++) {
+    const double* r = ci + (int64_t)j * m;
+    uint64_t mask = 0;
+    for (int i = 0; i < m; i++) {
+      uint64_t bits;
+      memcpy(&bits, &r[i], 8);
+      mask |= (uint64_t)((bits << 1) != 0) << i;
+    }
+    dup |= seen & mask;
+    seen |= mask;
+    scatter_row(mask, j, r, val, row);
+  }
+  return dup != 0;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) int pack_one_avx2(int n, int m, const double* __restrict__ ci, double* __restrict__ val,
+                                                  uint8_t* __restrict__ row) {
+  const __m256d zero = _mm256_setzero_pd();
+  int i = 0;
+  for (; i + 4 <= m; i += 4) _mm256_storeu_pd(val + i, zero);
+  for (; i < m; i++) val[i] = 0.0;
+  memset(row, 0, (size_t)m);
+  uint64_t seen = 0, dup = 0;
+  for (int j = 0; j < n; j++) {
+    const double* r = ci + (int64_t)j * m;
+    uint64_t mask = 0;
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+      const __m256d v = _mm256_loadu_pd(r + k);
+      mask |= (uint64_t)_mm256_movemask_pd(_mm256_cmp_pd(v, zero, _CMP_NEQ_UQ)) << k;
+    }
+    for (; k < m; k++) {
+      uint64_t bits;
+      memcpy(&bits, &r[k], 8);
+      mask |= (uint64_t)((bits << 1) != 0) << k;
+    }
+    dup |= seen & mask;
+    seen |= mask;
+    scatter_row(mask, j, r, val, row);
+  }
+  return dup != 0;
+}
+#define MGQP_HAVE_AVX2_PACK 1
+#endif
+
+typedef int (*pack_fn)(int, int, const double*, double*, uint8_t*);
+pack_fn pick_pack() {
+#ifdef MGQP_HAVE_AVX2_PACK
+  if (__builtin_cpu_supports("avx2")) return pack_one_avx2;
+#endif
+  return pack_one_generic;
+}
+
+}  // namespace
+
+namespace {
+
+// A small persistent pool: the host pipeline packs one chunk (tens of thousands of QPs, ~2 ms of
+// work) at a time, far too often to create threads for each.  One job at a time; the caller works too.
+class Pool {
+ public:
+  explicit Pool(int workers) {
+    for (int i = 0; i < workers; i++) th_.emplace_back([this]() { loop(); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int workers() const { return (int)th_.size(); }
+  // run job() on `extra` pool threads and on the calling thread
+  void run(const std::function<void()>& job, int extra) {
+    std::lock_guard<std::mutex> one(call_mu_);
+    if (extra > (int)th_.size()) extra = (int)th_.size();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &job;
+      want_ = extra;
+      pending_ = extra;
+      gen_++;
+    }
+    cv_.notify_all();
+    job();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this]() { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void loop() {
+    long seen = 0;
+    for (;;) {
+      const std::function<void()>* job = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return stop_ || (gen_ != seen && want_ > 0); });
+        if (stop_) return;
+        seen = gen_;
+        want_--;
+        job = job_;
+      }
+      (*job)();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_--;
+      }
+      done_.notify_all();
+    }
+  }
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> th_;
+  const std::function<void()>* job_ = nullptr;
+  long gen_ = 0;
+  int want_ = 0, pending_ = 0;
+  bool stop_ = false;
+};
+
+int default_threads() {
+  if (const char* e = getenv("MGQP_HOST_THREADS")) {
+    const int t = atoi(e);
+    if (t >= 1) return t > 64 ? 64 : t;
+  }
+  int t = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) {  // a container may own fewer cores than the machine has
+    const int a = CPU_COUNT(&set);
+    if (a >= 1 && a < t) t = a;
+  }
+#endif
+  if (t < 1) t = 1;
+  return t > 64 ? 64 : t;
+}
+
+Pool& pool() {
+  static Pool p(default_threads() - 1);
+  return p;
+}
+
+}  // namespace
+
+extern "C" int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI, double* val,
+                                       int64_t sv, uint8_t* row, int64_t sr, int threads) {
+  if (n < 1 || n > 255 || m < 0 || m > 64 || count < 0) return 0;
+  if (count == 0 || m == 0) return 1;
+  static const pack_fn pack_one = pick_pack();
+  if (threads <= 0) threads = default_threads();
+  const int64_t block = 512;
+  const int64_t blocks = (count + block - 1) / block;
+  if (threads > blocks) threads = (int)blocks;
+  std::atomic<int64_t> next(0);
+  std::atomic<int> dense(0);
+  const std::function<void()> work = [&]() {
+    for (;;) {
+      const int64_t b = next.fetch_add(1);
+      if (b >= blocks || dense.load(std::memory_order_relaxed)) break;
+      const int64_t q1 = (b + 1) * block < count ? (b + 1) * block : count;
+      int bad = 0;
+      for (int64_t q = b * block; q < q1; q++) bad |= pack_one(n, m, CI + q * sCI, val + q * sv, row + q * sr);
+      if (bad) dense.store(1, std::memory_order_relaxed);
+    }
+  };
+  if (threads <= 1) work();
+  else pool().run(work, threads - 1);
+  return dense.load() ? 0 : 1;
+}

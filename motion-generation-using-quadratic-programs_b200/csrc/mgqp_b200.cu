@@ -28,6 +28,7 @@ namespace {
 using namespace mgqp;
 
 thread_local std::string g_last_error;
+thread_local long long g_h2d_bytes = 0, g_d2h_bytes = 0;  // of the calling thread's last host-buffer call
 std::atomic<long long> g_launches{0};
 
 int fail(int rc, const char* fmt, ...) {
@@ -68,6 +69,9 @@ struct DeviceCtx {
   cudaStream_t host_st[2] = {nullptr, nullptr};
   void* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
+  // pinned host staging for the column-compressed CI of one chunk (values, rows), per buffer set
+  void* pack_host[2] = {nullptr, nullptr};
+  size_t pack_cap[2] = {0, 0};
 };
 DeviceCtx g_dev[kMaxDev];
 
@@ -277,8 +281,11 @@ int validate(const mgqp_batch* d) {
   if (d->n < 1) return fail(MGQP_ERR_INVALID_ARG, "n = %d must be >= 1", d->n);
   if (d->p < 0 || d->m < 0) return fail(MGQP_ERR_INVALID_ARG, "p = %d, m = %d must be >= 0", d->p, d->m);
   if (d->batch < 0) return fail(MGQP_ERR_INVALID_ARG, "batch = %lld must be >= 0", (long long)d->batch);
-  if (!d->G || !d->g0 || (d->p && (!d->CE || !d->ce0)) || (d->m && (!d->CI || !d->ci0)))
+  if (!d->G || !d->g0 || (d->p && (!d->CE || !d->ce0)) || (d->m && ((!d->CI && !d->CI_val) || !d->ci0)))
     return fail(MGQP_ERR_INVALID_ARG, "null input pointer");
+  if (d->CI_val && d->m && !d->CI_row) return fail(MGQP_ERR_INVALID_ARG, "CI_val without CI_row");
+  if (d->CI_val && (d->sCIv < 0 || d->sCIr < 0 || (d->sCIv && d->sCIv < d->m) || (d->sCIr && d->sCIr < d->m)))
+    return fail(MGQP_ERR_INVALID_ARG, "bad stride of the column-compressed CI");
   if (!d->x || !d->f || !d->status) return fail(MGQP_ERR_INVALID_ARG, "null output pointer (x, f, status are required)");
   if (d->p > d->n)
     return fail(MGQP_ERR_INVALID_ARG, "p = %d equalities on n = %d variables (the reference indexes R out of bounds there)",
@@ -324,9 +331,18 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
       L.x = d->x; L.f = d->f; L.status = d->status; L.iq = d->iq; L.A = d->A; L.iters = d->iters;
       L.max_iter = max_iter;
       L.ticket = ticket;
+      if (d->CI_val && d->m) {
+        L.ci_val = d->CI_val;
+        L.ci_row = d->CI_row;
+        L.s_ci_val = d->sCIv;
+        L.s_ci_row = d->sCIr;
+      }
       return fast ? launch_lane_n<true>(ctx, lp, L, st) : launch_lane_n<false>(ctx, lp, L, st);
     }
   }
+  if (d->CI_val && d->m)
+    return fail(MGQP_ERR_UNSUPPORTED_SHAPE,
+                "column-compressed CI is served by the one-QP-per-lane kernel only (n <= 8, m <= 64, no kernel-forcing flag)");
   const Plan pl = (d->flags & MGQP_FLAG_CTA_KERNEL) ? Plan() : make_plan(d->n, d->p, d->m, ctx->smem_optin);
   if (pl.gw < 0) {
     const LargePlan lp = make_large_plan(d->n, d->p, d->m, ctx->smem_optin);
@@ -393,7 +409,14 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
 struct DevBufs {
   double *G = nullptr, *g0 = nullptr, *CE = nullptr, *ce0 = nullptr, *CI = nullptr, *ci0 = nullptr, *x = nullptr, *f = nullptr;
   int *status = nullptr, *iq = nullptr, *A = nullptr, *iters = nullptr;
+  double* CIv = nullptr;          // column-compressed CI of the chunk
+  unsigned char* CIr = nullptr;
+  double* hCIv = nullptr;         // its pinned host staging (packer output)
+  unsigned char* hCIr = nullptr;
 };
+
+// rows of the compressed form are padded so that every QP's block stays 16-byte aligned
+inline long long packed_row_stride(long long m) { return (m + 15) & ~15ll; }
 
 // Carve the staging buffers of one chunk out of one arena (256-byte aligned pieces).
 size_t carve_bufs(DevBufs& b, const mgqp_batch* h, long long chunk, char* base) {
@@ -416,31 +439,64 @@ size_t carve_bufs(DevBufs& b, const mgqp_batch* h, long long chunk, char* base) 
   b.iq = (int*)take(chunk * 4);
   b.A = (int*)take(chunk * (p + m) * 4);
   b.iters = (int*)take(chunk * 4);
+  b.CIv = (double*)take(chunk * m * 8);
+  b.CIr = (unsigned char*)take(chunk * packed_row_stride(m));
   return off;
 }
 
 // Upload / solve / download QPs [q0, q0+cnt) of host batch h through buffers b on stream st.
-int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long long cnt, cudaStream_t st) {
+// `pack`: the shape is served by the lane kernel and the caller did not opt out, so CI travels in
+// column-compressed form whenever this chunk qualifies (every column a bound on one variable).
+int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long long cnt, cudaStream_t st, bool pack) {
   const long long n = h->n, p = h->p, m = h->m;
+  const long long mr = packed_row_stride(m);
   mgqp_batch d = *h;
   d.batch = cnt;
+  d.CI_val = nullptr; d.CI_row = nullptr; d.sCIv = 0; d.sCIr = 0;
+  bool ci_compressed = false;
+  if (m > 0 && h->CI_val) {  // the caller's own compressed form: ship it as it is
+    const long long cv = h->sCIv ? cnt : 1, cr = h->sCIr ? cnt : 1;
+    if (h->sCIv == 0 || h->sCIv == m) {
+      CU(cudaMemcpyAsync(b.CIv, h->CI_val + q0 * h->sCIv, (size_t)(cv * m) * 8, cudaMemcpyHostToDevice, st));
+    } else {
+      CU(cudaMemcpy2DAsync(b.CIv, (size_t)m * 8, h->CI_val + q0 * h->sCIv, (size_t)h->sCIv * 8, (size_t)m * 8, (size_t)cv,
+                           cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpy2DAsync(b.CIr, (size_t)mr, h->CI_row + q0 * h->sCIr, (size_t)(h->sCIr ? h->sCIr : m), (size_t)m, (size_t)cr,
+                         cudaMemcpyHostToDevice, st));
+    g_h2d_bytes += cv * m * 8 + cr * m;
+    d.CI_val = b.CIv; d.CI_row = b.CIr;
+    d.sCIv = h->sCIv ? m : 0; d.sCIr = h->sCIr ? mr : 0;
+    ci_compressed = true;
+  } else if (m > 0 && pack && b.hCIv &&
+             mgqp_pack_bound_columns((int32_t)n, (int32_t)m, cnt, h->CI + q0 * h->sCI, h->sCI, b.hCIv, m, b.hCIr, mr, 0)) {
+    CU(cudaMemcpyAsync(b.CIv, b.hCIv, (size_t)(cnt * m) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b.CIr, b.hCIr, (size_t)(cnt * mr), cudaMemcpyHostToDevice, st));
+    g_h2d_bytes += cnt * m * 8 + cnt * mr;
+    d.CI_val = b.CIv; d.CI_row = b.CIr; d.sCIv = m; d.sCIr = mr;
+    ci_compressed = true;
+  }
   struct F { const double* src; long long stride, size; double* dst; const double** dptr; int64_t* dstride; };
   F fs[6] = {{h->G, h->sG, n * n, b.G, &d.G, &d.sG},       {h->g0, h->sg0, n, b.g0, &d.g0, &d.sg0},
              {h->CE, h->sCE, n * p, b.CE, &d.CE, &d.sCE},  {h->ce0, h->sce0, p, b.ce0, &d.ce0, &d.sce0},
              {h->CI, h->sCI, n * m, b.CI, &d.CI, &d.sCI},  {h->ci0, h->sci0, m, b.ci0, &d.ci0, &d.sci0}};
-  for (auto& f : fs) {
+  for (int k = 0; k < 6; k++) {
+    F& f = fs[k];
     *f.dptr = f.dst;
-    if (f.size == 0) { *f.dstride = 0; continue; }
+    if (f.size == 0 || (k == 4 && ci_compressed)) { *f.dstride = 0; continue; }
     if (f.stride == 0) {  // broadcast field: one instance
       CU(cudaMemcpyAsync(f.dst, f.src, (size_t)f.size * 8, cudaMemcpyHostToDevice, st));
       *f.dstride = 0;
+      g_h2d_bytes += f.size * 8;
     } else if (f.stride == f.size) {
       CU(cudaMemcpyAsync(f.dst, f.src + q0 * f.stride, (size_t)(cnt * f.size) * 8, cudaMemcpyHostToDevice, st));
       *f.dstride = f.size;
+      g_h2d_bytes += cnt * f.size * 8;
     } else {  // padded host layout: compact it on the way up
       CU(cudaMemcpy2DAsync(f.dst, (size_t)f.size * 8, f.src + q0 * f.stride, (size_t)f.stride * 8, (size_t)f.size * 8,
                            (size_t)cnt, cudaMemcpyHostToDevice, st));
       *f.dstride = f.size;
+      g_h2d_bytes += cnt * f.size * 8;
     }
   }
   d.x = b.x; d.f = b.f; d.status = b.status;
@@ -452,9 +508,13 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
   CU(cudaMemcpyAsync(h->x + q0 * n, b.x, (size_t)(cnt * n) * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->f + q0, b.f, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h->status + q0, b.status, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
-  if (h->iq) CU(cudaMemcpyAsync(h->iq + q0, b.iq, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
-  if (h->A) CU(cudaMemcpyAsync(h->A + q0 * (p + m), b.A, (size_t)(cnt * (p + m)) * 4, cudaMemcpyDeviceToHost, st));
-  if (h->iters) CU(cudaMemcpyAsync(h->iters + q0, b.iters, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+  g_d2h_bytes += cnt * (n * 8 + 8 + 4);
+  if (h->iq) { CU(cudaMemcpyAsync(h->iq + q0, b.iq, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st)); g_d2h_bytes += cnt * 4; }
+  if (h->A) {
+    CU(cudaMemcpyAsync(h->A + q0 * (p + m), b.A, (size_t)(cnt * (p + m)) * 4, cudaMemcpyDeviceToHost, st));
+    g_d2h_bytes += cnt * (p + m) * 4;
+  }
+  if (h->iters) { CU(cudaMemcpyAsync(h->iters + q0, b.iters, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st)); g_d2h_bytes += cnt * 4; }
   return MGQP_OK;
 }
 
@@ -489,6 +549,24 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     }
     carve_bufs(bufs[i], h, chunk, static_cast<char*>(ctx->arena[i]));
   }
+  // CI goes up in column-compressed form where the lane kernel serves the shape (see run_chunk)
+  const bool pack = !(h->flags & (MGQP_FLAG_NO_HOST_PACK | MGQP_FLAG_GROUP_KERNEL | MGQP_FLAG_CTA_KERNEL)) && !h->CI_val &&
+                    h->m > 0 && h->sCI != 0 && make_lane_plan(h->n, h->p, h->m, ctx->smem_optin).ok;
+  if (pack) {
+    const size_t vbytes = ((size_t)chunk * h->m * 8 + 255) & ~(size_t)255;
+    const size_t pneed = vbytes + (size_t)chunk * packed_row_stride(h->m);
+    for (int i = 0; i < 2; i++) {
+      if (ctx->pack_cap[i] < pneed) {
+        if (ctx->pack_host[i]) CU(cudaFreeHost(ctx->pack_host[i]));
+        ctx->pack_host[i] = nullptr;
+        ctx->pack_cap[i] = 0;
+        CU(cudaHostAlloc(&ctx->pack_host[i], pneed, cudaHostAllocDefault));
+        ctx->pack_cap[i] = pneed;
+      }
+      bufs[i].hCIv = static_cast<double*>(ctx->pack_host[i]);
+      bufs[i].hCIr = static_cast<unsigned char*>(ctx->pack_host[i]) + vbytes;
+    }
+  }
   cudaStream_t* st = ctx->host_st;
   int k = 0;
   while (!rc) {
@@ -497,7 +575,7 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     const long long cnt = (h->batch - q0) < chunk ? (h->batch - q0) : chunk;
     // the buffer set is reused every second chunk: wait for its previous occupant
     if (cudaStreamSynchronize(st[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "stream sync failed"); break; }
-    rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1]);
+    rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1], pack);
     k++;
   }
   for (int i = 0; i < 2; i++) {
@@ -517,6 +595,7 @@ int solve_quadprog_batched(const mgqp_batch* d, int device, void* stream) {
 }
 
 int solve_quadprog_batched_host(const mgqp_batch* h, int device, int64_t chunk) {
+  g_h2d_bytes = g_d2h_bytes = 0;
   int rc = validate(h);
   if (rc) return rc;
   if (chunk <= 0) chunk = default_chunk(h);
@@ -534,15 +613,21 @@ int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int nd
     while (chunk > 1024 && h->batch / chunk < 4ll * ndev) chunk /= 2;
   }
   std::atomic<long long> next(0);
+  std::atomic<long long> up(0), down(0);
   std::vector<int> rcs(ndev, 0);
   std::vector<std::string> errs(ndev);
   std::vector<std::thread> th;
   for (int i = 0; i < ndev; i++)
     th.emplace_back([&, i]() {
+      g_h2d_bytes = g_d2h_bytes = 0;
       rcs[i] = pump(h, devices[i], chunk, &next);
       if (rcs[i]) errs[i] = g_last_error;
+      up += g_h2d_bytes;
+      down += g_d2h_bytes;
     });
   for (auto& t : th) t.join();
+  g_h2d_bytes = up.load();
+  g_d2h_bytes = down.load();
   for (int i = 0; i < ndev; i++)
     if (rcs[i]) return fail(rcs[i], "device %d: %s", devices[i], errs[i].c_str());
   return MGQP_OK;
@@ -597,6 +682,11 @@ const char* mgqp_status_string(int status) {
 }
 
 const char* mgqp_last_error(void) { return g_last_error.c_str(); }
+
+void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h) {
+  if (h2d) *h2d = g_h2d_bytes;
+  if (d2h) *d2h = g_d2h_bytes;
+}
 
 int mgqp_device_count(void) {
   int c = 0;

@@ -86,10 +86,24 @@ void lane_one(const LaneView& v, double* S, const LaneIO& io, int max_iter, int 
 }
 }  // namespace
 
+// CIv / CIr (optional): the column-compressed form of CI (mgqp_batch::CI_val / CI_row), [batch][m] each
+extern "C" int emu_lane_solve_batch_c(int n, int p, int m, long long batch, const double* G, const double* g0,
+                                      const double* CE, const double* ce0, const double* CI, const double* ci0,
+                                      double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
+                                      int fma, const double* CIv, const unsigned char* CIr);
+
 extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const double* G, const double* g0,
                                     const double* CE, const double* ce0, const double* CI, const double* ci0,
                                     double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
                                     int fma) {
+  return emu_lane_solve_batch_c(n, p, m, batch, G, g0, CE, ce0, CI, ci0, x, f, status, iq, A, iters, max_iter, fma,
+                                nullptr, nullptr);
+}
+
+extern "C" int emu_lane_solve_batch_c(int n, int p, int m, long long batch, const double* G, const double* g0,
+                                      const double* CE, const double* ce0, const double* CI, const double* ci0,
+                                      double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
+                                      int fma, const double* CIv, const unsigned char* CIr) {
   if (n < 1 || n > 8 || m > 64 || p > n) return -2;
   const LaneView v = make_lane_view(n, p, m);
   if (max_iter <= 0) max_iter = 100 + 10 * (p + m);
@@ -97,7 +111,11 @@ extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const 
   for (long long b = 0; b < batch; b++) {
     double* S = slot.data();
     for (int i = 0; i < v.stride; i++) S[i] = -1e300;  // poison
-    LaneIO io{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI + b * n * m, ci0 + b * m};
+    LaneIO io{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI ? CI + b * n * m : nullptr, ci0 + b * m};
+    if (CIv) {
+      io.CIv = CIv + b * m;
+      io.CIr = CIr + b * m;
+    }
     double xo[8];
     double fo;
     int st, q, it;

@@ -12,18 +12,37 @@ from mgqp_b200 import workloads
 from test_emu_lockstep import _degenerate_batch
 
 
-def lane_solve(lib, b, max_iter=0, fma=0):
+def lane_solve(lib, b, max_iter=0, fma=0, compressed=None):
+    """compressed = (val [B,m], row [B,m] uint8): solve from the column-compressed form of CI (the dense
+    block is then withheld from the solver altogether)."""
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
-    lib.emu_lane_solve_batch.restype = C.c_int
-    lib.emu_lane_solve_batch.argtypes = [C.c_int] * 3 + [C.c_longlong] + [dp] * 8 + [ip] * 4 + [C.c_int] * 2
+    lib.emu_lane_solve_batch_c.restype = C.c_int
+    lib.emu_lane_solve_batch_c.argtypes = [C.c_int] * 3 + [C.c_longlong] + [dp] * 8 + [ip] * 4 + [C.c_int] * 2 + [C.c_void_p] * 2
     B, n, p, m = b.batch, b.n, b.p, b.m
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in b.fields()]
     x = np.zeros((B, n)); f = np.zeros(B)
     st = np.zeros(B, np.int32); iq = np.zeros(B, np.int32); A = np.zeros((B, p + m), np.int32); it = np.zeros(B, np.int32)
-    rc = lib.emu_lane_solve_batch(n, p, m, B, *[a.ctypes.data_as(dp) for a in arrs], x.ctypes.data_as(dp),
-                                  f.ctypes.data_as(dp), *[a.ctypes.data_as(ip) for a in (st, iq, A, it)], max_iter, fma)
+    ptrs = [a.ctypes.data_as(dp) for a in arrs]
+    civ = cir = None
+    if compressed is not None:
+        val = np.ascontiguousarray(compressed[0], dtype=np.float64)
+        row = np.ascontiguousarray(compressed[1], dtype=np.uint8)
+        civ, cir = val.ctypes.data, row.ctypes.data
+        ptrs[4] = None
+    rc = lib.emu_lane_solve_batch_c(n, p, m, B, *ptrs, x.ctypes.data_as(dp),
+                                    f.ctypes.data_as(dp), *[a.ctypes.data_as(ip) for a in (st, iq, A, it)], max_iter, fma,
+                                    civ, cir)
     assert rc == 0
     return dict(x=x, f=f, status=st, iq=iq, A=A, iters=it)
+
+
+def _compress(CI):
+    """numpy restatement of the column compression (test-side, independent of the library's packer)."""
+    nz = (CI != 0) | np.isnan(CI)
+    assert (nz.sum(axis=1) <= 1).all(), "not a bound-only batch"
+    row = nz.argmax(axis=1).astype(np.uint8)                      # [B, m]
+    val = np.take_along_axis(CI, row[:, None, :].astype(np.int64), axis=1)[:, 0, :]
+    return np.where(nz.any(axis=1), val, 0.0), row
 
 
 def _oracle(restatement, b, max_iter=0):
@@ -88,3 +107,25 @@ def test_non_finite_cholesky_factor(emu_lib, restatement):
     assert np.array_equal(got["status"], ref["status"])
     assert np.array_equal(got["x"], ref["x"], equal_nan=True) and np.array_equal(got["f"], ref["f"], equal_nan=True)
     assert np.array_equal(got["iters"], ref["iters"])
+
+
+@pytest.mark.parametrize("name,B", [("C2", 3000), ("C5", 3000)])
+def test_column_compressed_constraints(emu_lib, restatement, name, B):
+    """mgqp_batch::CI_val / CI_row: the solver never sees the dense block, results stay bit-identical."""
+    b = workloads.make(name, B)
+    b.ci0[3::41, 5] = np.nan            # non-finite data takes the full-sum scan path
+    b.g0[4::43, 1] = np.inf
+    b.CI[5::47, :, 9] = 0.0             # an all-zero column
+    b.CI[6::53, 2, 2] = -0.0
+    assert_bit_identical(lane_solve(emu_lib, b, compressed=_compress(b.CI)), _oracle(restatement, b), name)
+
+
+def test_column_compressed_odd_shapes(emu_lib, restatement):
+    for n, p, m in [(5, 1, 11), (8, 2, 16), (3, 0, 6), (7, 1, 63)]:
+        b = workloads.make_random(200, n, p, m, seed=7 * n + m)
+        rng = np.random.default_rng(m)
+        rows = rng.integers(0, n, size=(b.batch, m))
+        vals = rng.choice([-1.0, 1.0, 0.5, -2.5], size=(b.batch, m))
+        b.CI[...] = 0.0
+        np.put_along_axis(b.CI, rows[:, None, :], vals[:, None, :], axis=1)
+        assert_bit_identical(lane_solve(emu_lib, b, compressed=_compress(b.CI)), _oracle(restatement, b), f"R{n}_{p}_{m}")

@@ -234,6 +234,52 @@ def test_host_buffer_entry_point(gpu, restatement):
     assert_bit_identical(r._asdict(), ref, "host")
 
 
+def test_column_compressed_device_input(gpu, restatement):
+    """mgqp_batch::CI_val / CI_row on device pointers: the dense CI block is never given to the kernel."""
+    import torch
+    for name, B in (("C2", 20001), ("C5", 10007)):
+        b = workloads.make(name, B)
+        b.ci0[3::41, 5] = np.nan
+        b.g0[4::43, 1] = np.inf
+        b.CI[5::47, :, 9] = 0.0
+        val, row = gpu.pack_bound_columns(b.CI)
+        t = _dev(b)
+        r = gpu.solve_quadprog_batched(t[0], t[1], t[2], t[3], None, t[5], want_active_set=True,
+                                       CI_val=torch.from_numpy(val).cuda(), CI_row=torch.from_numpy(row).cuda())
+        torch.cuda.synchronize()
+        assert_bit_identical({k: v.cpu().numpy() for k, v in r._asdict().items()}, _oracle(restatement, b), name)
+    b = workloads.make("S2", 64)  # n = 14: not a lane-kernel shape
+    val = torch.zeros((64, b.m), dtype=torch.float64, device="cuda")
+    row = torch.zeros((64, b.m), dtype=torch.uint8, device="cuda")
+    t = _dev(b)
+    with pytest.raises(NotImplementedError):
+        gpu.solve_quadprog_batched(*t, CI_val=val, CI_row=row)
+
+
+def test_host_pipeline_compressed_transport(gpu, restatement):
+    """The host-buffer entry point ships CI column-compressed chunk by chunk when it can, dense when it
+    cannot; either way the results are those of the oracle, bit for bit."""
+    b = workloads.make("C5", 40001)
+    ref = _oracle(restatement, b)
+    r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=4096)
+    up_packed, down = gpu.last_transfer_bytes()
+    assert_bit_identical(r._asdict(), ref, "packed")
+    r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=4096, flags=gpu.FLAG_NO_HOST_PACK)
+    up_dense, _ = gpu.last_transfer_bytes()
+    assert_bit_identical(r._asdict(), ref, "dense")
+    B, n, p, m = b.batch, b.n, b.p, b.m
+    assert up_dense == 8 * B * (n * n + n + n * p + p + n * m + m)
+    assert up_packed == 8 * B * (n * n + n + n * p + p + m + m) + B * ((m + 15) // 16 * 16)
+    assert down == B * (8 * n + 8 + 4 + 4 + 4 * (p + m) + 4)
+    # a batch in which only some chunks qualify: QPs 10000.. get a second nonzero in one column
+    b.CI[10000:, 2, 5] = 0.25
+    ref = _oracle(restatement, b)
+    r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=4096)
+    up_mixed, _ = gpu.last_transfer_bytes()
+    assert_bit_identical(r._asdict(), ref, "mixed")
+    assert up_packed < up_mixed < up_dense
+
+
 def test_multi_device_entry_point(gpu, restatement):
     import torch
     devs = list(range(torch.cuda.device_count()))

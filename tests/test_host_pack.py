@@ -1,0 +1,67 @@
+"""CPU: the host side of the column-compressed constraint transport (mgqp_pack_bound_columns in
+include/mgqp_b200.h) -- a codec, no QP arithmetic: decoding its output must give back the dense CI
+block, and anything that is not a bound on one variable must be refused."""
+import numpy as np
+import pytest
+
+from mgqp_b200 import workloads
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    import mgqp_b200
+    return mgqp_b200
+
+
+def _decode(val, row, n):
+    B, m = val.shape
+    CI = np.zeros((B, n, m))
+    np.put_along_axis(CI, row[:, None, :].astype(np.int64), val[:, None, :], axis=1)
+    return CI
+
+
+@pytest.mark.parametrize("name", ["C2", "C5"])
+@pytest.mark.parametrize("threads", [1, 0])
+def test_round_trip_on_the_headline_shapes(lib, name, threads):
+    b = workloads.make(name, 5003)
+    out = lib.pack_bound_columns(b.CI, threads=threads)
+    assert out is not None
+    val, row = out
+    assert val.shape == (b.batch, b.m) and row.dtype == np.uint8 and (row < b.n).all()
+    assert np.array_equal(_decode(val, row, b.n), b.CI)
+
+
+def test_random_bound_columns_zero_columns_signed_zeros_and_nan(lib):
+    rng = np.random.default_rng(5)
+    for n, m in [(1, 1), (3, 6), (5, 11), (7, 42), (8, 64), (8, 63)]:
+        B = 257
+        rows = rng.integers(0, n, size=(B, m))
+        vals = rng.standard_normal((B, m))
+        CI = np.zeros((B, n, m))
+        np.put_along_axis(CI, rows[:, None, :], vals[:, None, :], axis=1)
+        CI[::7, :, 0] = 0.0                      # empty column
+        CI[1::7, :, m - 1] = 0.0
+        CI[1::7, n - 1, m - 1] = np.nan          # NaN is a nonzero
+        CI[2::7][CI[2::7] == 0] = -0.0           # negative zeros stay zeros
+        val, row = lib.pack_bound_columns(CI)
+        dec = _decode(val, row, n)
+        assert np.array_equal(dec, CI, equal_nan=True), (n, m)
+        assert (val[::7, 0] == 0).all()
+
+
+def test_refuses_columns_with_two_nonzeros(lib):
+    b = workloads.make("C2", 4096)
+    assert lib.pack_bound_columns(b.CI) is not None
+    b.CI[4095, 4, 17] = 1e-300                   # one extra entry in the very last QP
+    assert b.CI[4095, :, 17].astype(bool).sum() == 2
+    assert lib.pack_bound_columns(b.CI) is None
+    assert lib.pack_bound_columns(workloads.make_random(100, 6, 1, 12, seed=3).CI) is None
+
+
+def test_empty_and_degenerate_sizes(lib):
+    assert lib.pack_bound_columns(np.zeros((0, 7, 42))) is not None
+    val, row = lib.pack_bound_columns(np.zeros((5, 7, 0)))
+    assert val.shape == (5, 0)
+    assert lib.pack_bound_columns(np.zeros((3, 7, 65))) is None      # beyond the lane kernel's m <= 64
