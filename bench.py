@@ -172,6 +172,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     import __graft_entry__ as g
     if not os.path.exists(g.LIB):
         g.build()
+    # one rank per GPU shares the box's host cores: the host packer of the e2e pipeline gets its share
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("MGQP_HOST_THREADS", str(max(1, host_threads() // max(1, local_world))))
     import mgqp_b200
     from mgqp_b200 import workloads
 

@@ -40,7 +40,8 @@ enum {
   MGQP_STATUS_INFEASIBLE = 1,   /* f = +inf, x = last iterate (as the reference leaves it)    */
   MGQP_STATUS_NOT_PD = 2,       /* f = the non-positive Cholesky pivot (for the error message) */
   MGQP_STATUS_EQ_DEPENDENT = 3, /* f, x = state when the dependent equality was met            */
-  MGQP_STATUS_ITER_CAP = 4
+  MGQP_STATUS_ITER_CAP = 4,
+  MGQP_STATUS_RETRIED = 16 /* bit, with MGQP_FLAG_RETRY_WITHOUT_CI only: the low bits are the retry's verdict */
 };
 
 /* Return codes of the entry points themselves (argument / CUDA errors; never a per-QP verdict). */
@@ -70,7 +71,15 @@ enum {
   MGQP_FLAG_CTA_KERNEL = 16,
   /* Host-buffer entry points only: ship CI to the device as it is (dense) instead of in the
    * column-compressed transport form described at mgqp_batch::CI_val. */
-  MGQP_FLAG_NO_HOST_PACK = 32
+  MGQP_FLAG_NO_HOST_PACK = 32,
+  /* The reference adapter's policy for an infeasible answer (solveNextStep, src/mgqp.cpp:717-735,
+   * TRY_TO_CONVERGE): every QP whose cost comes back NaN or +inf is solved again WITHOUT its
+   * inequalities, on the G the first call left behind -- its Cholesky factor, mirrored
+   * (QuadProg++.hh:42-45; the identity for the reference's own G = I) -- and if that answer is
+   * NaN / +inf too, x is zeroed (:732).  Such QPs come back with MGQP_STATUS_RETRIED or-ed into
+   * their status (16 = solved by the retry, 17 = lost twice, x = 0; 18 / 19 = the retry ran into
+   * one of the reference's exceptions).  The call synchronises its stream once. */
+  MGQP_FLAG_RETRY_WITHOUT_CI = 64
 };
 
 /* One batch of `batch` independent QPs of one shape, field-wise SoA, DEVICE pointers.

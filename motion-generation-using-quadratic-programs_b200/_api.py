@@ -28,7 +28,7 @@ __all__ = [
     "LogicError", "QPResult", "STATUS", "lib", "lib_path", "solve_quadprog", "solve_quadprog_batched",
     "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
     "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL",
-    "FLAG_NO_HOST_PACK", "mgqp_batch", "pack_bound_columns", "last_transfer_bytes",
+    "FLAG_NO_HOST_PACK", "FLAG_RETRY_WITHOUT_CI", "STATUS_RETRIED", "mgqp_batch", "pack_bound_columns", "last_transfer_bytes",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -38,6 +38,8 @@ FLAG_STATIC_SCHEDULE = 4
 FLAG_GROUP_KERNEL = 8
 FLAG_CTA_KERNEL = 16
 FLAG_NO_HOST_PACK = 32
+FLAG_RETRY_WITHOUT_CI = 64
+STATUS_RETRIED = 16
 STATUS = {0: "ok", 1: "infeasible", 2: "not_pd", 3: "eq_dependent", 4: "iter_cap"}
 
 

@@ -22,6 +22,7 @@
 #include "gi_lane_kernel.cuh"
 #include "gi_large_kernel.cuh"
 #include "gi_small_kernel.cuh"
+#include "retry.cuh"
 
 namespace {
 
@@ -295,7 +296,7 @@ int validate(const mgqp_batch* d) {
   return MGQP_OK;
 }
 
-int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
+int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
   int rc = validate(d);
   if (rc) return rc;
   if (d->batch == 0) return MGQP_OK;
@@ -403,6 +404,82 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   if (pl.gw == 8) return fast ? launch_small<8, true>(ctx, pl, P, st, gi, 1) : launch_small<8, false>(ctx, pl, P, st, gi, 0);
   if (pl.gw == 16) return fast ? launch_small<16, true>(ctx, pl, P, st, gi, 1) : launch_small<16, false>(ctx, pl, P, st, gi, 0);
   return fast ? launch_small<32, true>(ctx, pl, P, st, gi, 1) : launch_small<32, false>(ctx, pl, P, st, gi, 0);
+}
+
+// The reference adapter's policy for an infeasible answer (src/mgqp.cpp:717-735), for a whole batch:
+// see retry.cuh.  Synchronises `st` once (the host has to learn how many QPs go round again).
+int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
+  if (!d || !(d->flags & MGQP_FLAG_RETRY_WITHOUT_CI)) return solve_device_once(d, device, st);
+  mgqp_batch first = *d;
+  first.flags &= ~MGQP_FLAG_RETRY_WITHOUT_CI;
+  int rc = solve_device_once(&first, device, st);
+  if (rc || d->batch == 0) return rc;
+  if (d->n > 1024) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "MGQP_FLAG_RETRY_WITHOUT_CI serves n <= 1024");
+  const long long B = d->batch, n = d->n, p = d->p, m = d->m;
+  long long* idx = nullptr;
+  unsigned long long* count = nullptr;
+  CU(cudaMallocAsync(&idx, (size_t)B * 8 + 8, st));
+  count = reinterpret_cast<unsigned long long*>(idx + B);
+  CU(cudaMemsetAsync(count, 0, 8, st));
+  retry_mark_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d->f, d->status, B, idx, count);
+  g_launches.fetch_add(1);
+  unsigned long long cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (cnt == 0) {
+    CU(cudaFreeAsync(idx, st));
+    return MGQP_OK;
+  }
+  // compact second batch: G' g0 CE ce0 | x f | status iq A iters
+  const long long c = (long long)cnt;
+  const size_t dbl = (size_t)c * (n * n + n + n * p + p + n + 1);
+  const size_t ints = (size_t)c * (3 + p);
+  double* ws = nullptr;
+  CU(cudaMallocAsync(&ws, dbl * 8 + ints * 4 + 64, st));
+  double* G2 = ws;
+  double* g02 = G2 + c * n * n;
+  double* CE2 = g02 + c * n;
+  double* ce02 = CE2 + c * n * p;
+  double* x2 = ce02 + c * p;
+  double* f2 = x2 + c * n;
+  int* st2 = reinterpret_cast<int*>(f2 + c);
+  int* iq2 = st2 + c;
+  int* it2 = iq2 + c;
+  int* A2 = it2 + c;
+  RetryGather g;
+  g.n = (int)n; g.p = (int)p;
+  g.G = d->G; g.g0 = d->g0; g.CE = d->CE; g.ce0 = d->ce0;
+  g.sG = d->sG; g.sg0 = d->sg0; g.sCE = d->sCE; g.sce0 = d->sce0;
+  g.G2 = G2; g.g02 = g02; g.CE2 = CE2; g.ce02 = ce02;
+  g.idx = idx; g.count = count;
+  {
+    const long long warps = c < 4096 ? c : 4096;
+    retry_gather_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(g);
+    g_launches.fetch_add(1);
+  }
+  mgqp_batch second;
+  memset(&second, 0, sizeof second);
+  second.n = (int32_t)n; second.p = (int32_t)p; second.m = 0; second.batch = c;
+  second.G = G2; second.g0 = g02; second.CE = CE2; second.ce0 = ce02;
+  second.sG = n * n; second.sg0 = n; second.sCE = n * p; second.sce0 = p;
+  second.x = x2; second.f = f2; second.status = st2; second.iq = iq2; second.A = p ? A2 : nullptr; second.iters = it2;
+  second.max_iter = d->max_iter;
+  second.flags = first.flags;
+  rc = solve_device_once(&second, device, st);
+  if (!rc) {
+    RetryScatter sc;
+    sc.n = (int)n; sc.pm = (int)(p + m); sc.p = (int)p;
+    sc.x2 = x2; sc.f2 = f2; sc.st2 = st2; sc.iq2 = iq2; sc.A2 = A2; sc.it2 = it2;
+    sc.x = d->x; sc.f = d->f; sc.status = d->status; sc.iq = d->iq; sc.A = d->A; sc.iters = d->iters;
+    sc.idx = idx; sc.count = count;
+    retry_scatter_kernel<<<(unsigned)((c + 127) / 128), 128, 0, st>>>(sc);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(MGQP_ERR_CUDA, "retry kernels failed: %s", cudaGetErrorString(e));
+  }
+  cudaFreeAsync(ws, st);
+  cudaFreeAsync(idx, st);
+  return rc;
 }
 
 // ------------------------------------------------------------------ host-buffer pipeline

@@ -280,6 +280,49 @@ def test_host_pipeline_compressed_transport(gpu, restatement):
     assert up_packed < up_mixed < up_dense
 
 
+def _retry_policy_expected(restatement, b, ref):
+    """solveNextStep's TRY_TO_CONVERGE policy (src/mgqp.cpp:717-735) restated with the oracle: the second
+    call runs without inequalities on the G object the first call overwrote with its Cholesky factor."""
+    exp = {k: v.copy() for k, v in ref.items()}
+    f = ref["f"]
+    again = np.nonzero(((f != f) | np.isposinf(f)) & (ref["status"] != 2) & (ref["status"] != 3))[0]
+    n, p, m = b.n, b.p, b.m
+    for q in again:
+        one = restatement.solve_one(b.G[q], b.g0[q], b.CE[q], b.ce0[q], b.CI[q], b.ci0[q], max_iter=default_max_iter(p, m))
+        assert one["status"] == ref["status"][q]
+        two = restatement.solve_one(one["G_factor"], b.g0[q], b.CE[q], b.ce0[q], np.zeros((n, 0)), np.zeros(0),
+                                    max_iter=default_max_iter(p, 0))
+        st, f2 = two["status"], two["f"]
+        lost = st not in (2, 3) and (f2 != f2 or f2 == np.inf)
+        exp["x"][q] = 0.0 if lost else two["x"]
+        exp["f"][q] = f2
+        exp["status"][q] = (1 if lost else st) | 16
+        exp["iq"][q] = two["iq"]
+        exp["iters"][q] = two["iters"]
+        exp["A"][q] = 0x7fffffff
+        exp["A"][q, :two["iq"]] = two["A"][:two["iq"]]
+    return exp, again
+
+
+@pytest.mark.parametrize("name,B,flags", [("C5", 6007, 0), ("C5", 6007, 8), ("S2", 3001, 0)])
+def test_infeasible_retry_policy_of_the_reference_adapter(gpu, restatement, name, B, flags):
+    b = workloads.make(name, B)
+    if name == "S2":                      # the shipped shape is always feasible: contradict a bound pair
+        b.ci0[::9, 3] = -7.0
+        b.ci0[::9, 3 + 14] = -7.0
+    b.ce0[5::97, 0] = np.nan              # NaN cost both times: the command is zeroed (status 17)
+    ref = _oracle(restatement, b)
+    exp, again = _retry_policy_expected(restatement, b, ref)
+    assert len(again) > 50 and (exp["status"] == 17).sum() >= B // 97 and (exp["status"] == 16).sum() > 20
+    assert (exp["x"][exp["status"] == 17] == 0).all()
+    got = _solve(gpu, b, flags=flags | gpu.FLAG_RETRY_WITHOUT_CI)
+    assert_bit_identical(got, exp, name)
+    assert ((got["status"] & 16) != 0).sum() == len(again)
+    # the host-buffer entry point applies the same policy chunk by chunk
+    r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=1024, flags=flags | gpu.FLAG_RETRY_WITHOUT_CI)
+    assert_bit_identical(r._asdict(), exp, name + " host")
+
+
 def test_multi_device_entry_point(gpu, restatement):
     import torch
     devs = list(range(torch.cuda.device_count()))
