@@ -106,7 +106,7 @@ typedef struct mgqp_batch {
    * builds (limitsMatrix = [-I; +I], src/mgqp.cpp:1080-1128).  When CI_val != NULL, CI / sCI are
    * ignored and column i of QP b is  CI_val[b*sCIv + i] * e_k  with  k = CI_row[b*sCIr + i] < n
    * (an all-zero column: value 0, any row).  m*9 bytes per QP instead of n*m*8.  Served by the
-   * one-QP-per-lane kernel (n <= 8, m <= 64); other shapes return MGQP_ERR_UNSUPPORTED_SHAPE.
+   * one-QP-per-lane and lane-group kernels (n <= 32); larger n returns MGQP_ERR_UNSUPPORTED_SHAPE.
    * The host-buffer entry points build this form themselves, chunk by chunk, on host threads
    * (mgqp_pack_bound_columns) whenever a chunk qualifies, so that the PCIe link carries 1.2 KB
    * instead of 3.2 KB per 7-DoF QP; results are bit-identical either way. */

@@ -24,6 +24,10 @@ struct SmallParams {
   int max_iter;
   unsigned* ticket;      // work-queue head (zeroed before launch); nullptr = static round robin
   int bar_bytes;         // bytes reserved for the per-warp mbarriers at the start of shared memory
+  // column-compressed CI (mgqp_batch::CI_val / CI_row) or null; when set, field 4 is not read at all
+  const double* ci_val;
+  const unsigned char* ci_row;
+  long long s_ci_val, s_ci_row;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -108,8 +112,27 @@ __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant_
     }
     // fields that cannot go through TMA (odd alignment, broadcast or padded strides, tail tile):
     // plain coalesced loads; groups beyond the tail replicate the tile's first QP
+    if (P.ci_val && P.size[4] > 0) {
+      // column-compressed constraints: rebuild the dense n x m block in shared memory (zeros, then one
+      // coefficient per column).  The kernel's sums start from +0.0, so a +0.0 where the caller's block
+      // had -0.0 cannot change any result.
+      const int n = P.tv.n, m = P.tv.m, sz = n * m;
+      double* ci = ws + P.off[4];
+#pragma unroll 1
+      for (int idx = lane; idx < QPW * sz; idx += 32) ci[idx] = 0.0;
+      __syncwarp();
+#pragma unroll 1
+      for (int idx = lane; idx < QPW * m; idx += 32) {
+        const int q = idx / m, i = idx - q * m;
+        const long long qq = q0 + (q < cnt ? q : 0);
+        unsigned r = __ldg(P.ci_row + qq * P.s_ci_row + i);
+        r = r < (unsigned)n ? r : (unsigned)(n - 1);
+        ci[q * sz + (int)r * m + i] = __ldg(P.ci_val + qq * P.s_ci_val + i);
+      }
+    }
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {  // cold path: keep it small (instruction-cache footprint)
+      if (k == 4 && P.ci_val) continue;
       if (!(bulk & (1u << k)) && P.size[k] > 0) {
         const int sz = P.size[k], tot = QPW * sz;
 #pragma unroll 1

@@ -341,11 +341,12 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
       return fast ? launch_lane_n<true>(ctx, lp, L, st) : launch_lane_n<false>(ctx, lp, L, st);
     }
   }
-  if (d->CI_val && d->m)
-    return fail(MGQP_ERR_UNSUPPORTED_SHAPE,
-                "column-compressed CI is served by the one-QP-per-lane kernel only (n <= 8, m <= 64, no kernel-forcing flag)");
+
   const Plan pl = (d->flags & MGQP_FLAG_CTA_KERNEL) ? Plan() : make_plan(d->n, d->p, d->m, ctx->smem_optin);
   if (pl.gw < 0) {
+    if (d->CI_val && d->m)
+      return fail(MGQP_ERR_UNSUPPORTED_SHAPE,
+                  "column-compressed CI is served by the lane and lane-group kernels only (n <= 32, no CTA-kernel flag)");
     const LargePlan lp = make_large_plan(d->n, d->p, d->m, ctx->smem_optin);
     if (!lp.ok)
       return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "shape n=%d p=%d m=%d needs %d B of shared memory per CTA", d->n, d->p,
@@ -385,7 +386,8 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
     P.off[k] = off[k];
     const long long bytes = (long long)qpw * size[k] * 8;
     const bool ok = !(d->flags & MGQP_FLAG_NO_BULK_COPY) && size[k] > 0 && stride[k] == size[k] &&
-                    (bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(in[k]) % 16) == 0;
+                    (bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(in[k]) % 16) == 0 &&
+                    !(k == 4 && d->CI_val);
     if (ok) {
       P.bulk_mask |= 1u << k;
       P.bulk_bytes += (unsigned)bytes;
@@ -398,6 +400,12 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
   P.A = d->A;
   P.iters = d->iters;
   P.max_iter = max_iter;
+  if (d->CI_val && d->m) {
+    P.ci_val = d->CI_val;
+    P.ci_row = d->CI_row;
+    P.s_ci_val = d->sCIv;
+    P.s_ci_row = d->sCIr;
+  }
   P.bar_bytes = pl.bar_bytes;
   P.ticket = ticket;
   const int gi = pl.gw == 8 ? 0 : pl.gw == 16 ? 1 : 2;
@@ -627,8 +635,9 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     carve_bufs(bufs[i], h, chunk, static_cast<char*>(ctx->arena[i]));
   }
   // CI goes up in column-compressed form where the lane kernel serves the shape (see run_chunk)
-  const bool pack = !(h->flags & (MGQP_FLAG_NO_HOST_PACK | MGQP_FLAG_GROUP_KERNEL | MGQP_FLAG_CTA_KERNEL)) && !h->CI_val &&
-                    h->m > 0 && h->sCI != 0 && make_lane_plan(h->n, h->p, h->m, ctx->smem_optin).ok;
+  const bool pack = !(h->flags & (MGQP_FLAG_NO_HOST_PACK | MGQP_FLAG_CTA_KERNEL)) && !h->CI_val && h->m > 0 &&
+                    h->m <= 64 && h->sCI != 0 &&
+                    (make_lane_plan(h->n, h->p, h->m, ctx->smem_optin).ok || make_plan(h->n, h->p, h->m, ctx->smem_optin).gw > 0);
   if (pack) {
     const size_t vbytes = ((size_t)chunk * h->m * 8 + 255) & ~(size_t)255;
     const size_t pneed = vbytes + (size_t)chunk * packed_row_stride(h->m);

@@ -248,9 +248,24 @@ def test_column_compressed_device_input(gpu, restatement):
                                        CI_val=torch.from_numpy(val).cuda(), CI_row=torch.from_numpy(row).cuda())
         torch.cuda.synchronize()
         assert_bit_identical({k: v.cpu().numpy() for k, v in r._asdict().items()}, _oracle(restatement, b), name)
-    b = workloads.make("S2", 64)  # n = 14: not a lane-kernel shape
-    val = torch.zeros((64, b.m), dtype=torch.float64, device="cuda")
-    row = torch.zeros((64, b.m), dtype=torch.uint8, device="cuda")
+    for name, B in (("S0", 3001), ("S2", 3003)):  # the shipped n = 14 shapes: lane-group kernel
+        b = workloads.make(name, B)
+        b.CI[2::31][b.CI[2::31] == 0] = -0.0
+        b.ci0[7::53, 4] = np.nan
+        val, row = gpu.pack_bound_columns(b.CI)
+        t = _dev(b)
+        r = gpu.solve_quadprog_batched(t[0], t[1], t[2], t[3], None, t[5], want_active_set=True,
+                                       CI_val=torch.from_numpy(val).cuda(), CI_row=torch.from_numpy(row).cuda())
+        torch.cuda.synchronize()
+        assert_bit_identical({k: v.cpu().numpy() for k, v in r._asdict().items()}, _oracle(restatement, b), name)
+        ref = _oracle(restatement, b)
+        r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=1024)
+        up, _ = gpu.last_transfer_bytes()
+        assert_bit_identical(r._asdict(), ref, name + " host")
+        assert up == 8 * B * (b.n * b.n + b.n + b.n * b.p + b.p + 2 * b.m) + B * ((b.m + 15) // 16 * 16)
+    b = workloads.make_random(8, 40, 2, 10, seed=1)  # n = 40: CTA-per-QP kernel, no compressed form there
+    val = torch.zeros((8, b.m), dtype=torch.float64, device="cuda")
+    row = torch.zeros((8, b.m), dtype=torch.uint8, device="cuda")
     t = _dev(b)
     with pytest.raises(NotImplementedError):
         gpu.solve_quadprog_batched(*t, CI_val=val, CI_row=row)
