@@ -78,7 +78,8 @@ enum {
    * (QuadProg++.hh:42-45; the identity for the reference's own G = I) -- and if that answer is
    * NaN / +inf too, x is zeroed (:732).  Such QPs come back with MGQP_STATUS_RETRIED or-ed into
    * their status (16 = solved by the retry, 17 = lost twice, x = 0; 18 / 19 = the retry ran into
-   * one of the reference's exceptions).  The call synchronises its stream once. */
+   * one of the reference's exceptions).  The call stays asynchronous: the second launch reads the
+   * number of QPs that go round again from device memory. */
   MGQP_FLAG_RETRY_WITHOUT_CI = 64
 };
 

@@ -23,6 +23,7 @@ struct LaneParams {
   double* x; double* f; int* status; int* iq; int* A; int* iters;
   int max_iter;
   unsigned* ticket;
+  const unsigned long long* batch_dev;  // if set: the number of QPs lives on the device (<= batch)
 };
 
 template <int N, bool FMA>
@@ -46,10 +47,16 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
     return (prev < 0) ? my_warp : prev + total_warps;
   };
 
+  long long batch = P.batch, tiles = P.tiles;
+  if (P.batch_dev) {
+    const long long b = (long long)*P.batch_dev;
+    batch = b < batch ? b : batch;
+    tiles = (batch + 31) / 32;
+  }
   long long tile = next_tile(-1);
-  while (tile < P.tiles) {
+  while (tile < tiles) {
     const long long q0 = tile * 32;
-    const long long rem = P.batch - q0;
+    const long long rem = batch - q0;
     const int cnt = rem < 32 ? (int)rem : 32;
     const long long tile_next = next_tile(tile);
     const long long myq = q0 + (lane < cnt ? lane : 0);

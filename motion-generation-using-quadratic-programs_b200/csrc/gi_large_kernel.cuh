@@ -14,6 +14,7 @@ struct LargeParams {
   int max_iter;
   unsigned* ticket;
   double* workspace;  // gridDim.x * v.ws_doubles
+  const unsigned long long* batch_dev;  // if set: the number of QPs lives on the device (<= batch)
 };
 
 template <bool FMA>
@@ -22,6 +23,11 @@ __global__ void __launch_bounds__(512, 1) gi_large_kernel(const __grid_constant_
   __shared__ long long s_next;
   double* ws = P.workspace + (size_t)blockIdx.x * P.v.ws_doubles;
   long long q = -1;
+  long long batch = P.batch;
+  if (P.batch_dev) {
+    const long long b = (long long)*P.batch_dev;
+    batch = b < batch ? b : batch;
+  }
   for (;;) {
     if (threadIdx.x == 0) {
       if (P.ticket) s_next = (long long)atomicAdd(P.ticket, 1u);
@@ -30,7 +36,7 @@ __global__ void __launch_bounds__(512, 1) gi_large_kernel(const __grid_constant_
     __syncthreads();
     q = s_next;
     __syncthreads();
-    if (q >= P.batch) break;
+    if (q >= batch) break;
     LaneIO io;
     io.G = P.in[0] + q * P.stride[0];
     io.g0 = P.in[1] + q * P.stride[1];

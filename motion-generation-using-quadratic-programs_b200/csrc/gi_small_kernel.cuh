@@ -28,6 +28,7 @@ struct SmallParams {
   const double* ci_val;
   const unsigned char* ci_row;
   long long s_ci_val, s_ci_row;
+  const unsigned long long* batch_dev;  // if set: the number of QPs lives on the device (<= batch)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -95,10 +96,16 @@ __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant_
     return t;
   };
 
+  long long batch = P.batch, tiles = P.tiles;
+  if (P.batch_dev) {
+    const long long b = (long long)*P.batch_dev;
+    batch = b < batch ? b : batch;
+    tiles = (batch + QPW - 1) / QPW;
+  }
   long long tile = next_tile(-1);
-  while (tile < P.tiles) {
+  while (tile < tiles) {
     const long long q0 = tile * QPW;
-    const long long rem = P.batch - q0;
+    const long long rem = batch - q0;
     const int cnt = rem < QPW ? (int)rem : QPW;
     const unsigned bulk = (cnt == QPW) ? P.bulk_mask : 0u;
 
@@ -145,8 +152,8 @@ __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant_
     }
     // ---- next ticket now; pull that tile towards L2 while this one is being solved
     const long long tile_next = next_tile(tile);
-    if (tile_next < P.tiles && lane < 6 && (P.bulk_mask & (1u << lane)) &&
-        (tile_next + 1) * QPW <= P.batch) {
+    if (tile_next < tiles && lane < 6 && (P.bulk_mask & (1u << lane)) &&
+        (tile_next + 1) * QPW <= batch) {
       bulk_prefetch_l2(P.in[lane] + tile_next * QPW * P.stride[lane], (unsigned)(QPW * P.size[lane] * 8));
     }
     if (bulk) {

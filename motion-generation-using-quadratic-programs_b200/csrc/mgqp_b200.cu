@@ -88,6 +88,15 @@ int device_ctx(int device, DeviceCtx** out) {
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    {
+      // stream-ordered workspaces (CTA-per-QP kernel, retry pass) are allocated per call: keep what they
+      // free in the device's pool instead of handing it back to the driver at every synchronisation
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    }
     CU(cudaMalloc(&c.tickets, kTicketRing * sizeof(unsigned)));
     CU(cudaMemset(c.tickets, 0, kTicketRing * sizeof(unsigned)));
     c.init = true;
@@ -296,7 +305,7 @@ int validate(const mgqp_batch* d) {
   return MGQP_OK;
 }
 
-int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
+int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const unsigned long long* batch_dev = nullptr) {
   int rc = validate(d);
   if (rc) return rc;
   if (d->batch == 0) return MGQP_OK;
@@ -332,6 +341,7 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
       L.x = d->x; L.f = d->f; L.status = d->status; L.iq = d->iq; L.A = d->A; L.iters = d->iters;
       L.max_iter = max_iter;
       L.ticket = ticket;
+      L.batch_dev = batch_dev;
       if (d->CI_val && d->m) {
         L.ci_val = d->CI_val;
         L.ci_row = d->CI_row;
@@ -364,6 +374,7 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
     L.x = d->x; L.f = d->f; L.status = d->status; L.iq = d->iq; L.A = d->A; L.iters = d->iters;
     L.max_iter = max_iter;
     L.ticket = ticket;
+    L.batch_dev = batch_dev;
     return fast ? launch_large<true>(ctx, lp, L, st) : launch_large<false>(ctx, lp, L, st);
   }
 
@@ -408,6 +419,7 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
   }
   P.bar_bytes = pl.bar_bytes;
   P.ticket = ticket;
+  P.batch_dev = batch_dev;
   const int gi = pl.gw == 8 ? 0 : pl.gw == 16 ? 1 : 2;
   if (pl.gw == 8) return fast ? launch_small<8, true>(ctx, pl, P, st, gi, 1) : launch_small<8, false>(ctx, pl, P, st, gi, 0);
   if (pl.gw == 16) return fast ? launch_small<16, true>(ctx, pl, P, st, gi, 1) : launch_small<16, false>(ctx, pl, P, st, gi, 0);
@@ -415,7 +427,8 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st) {
 }
 
 // The reference adapter's policy for an infeasible answer (src/mgqp.cpp:717-735), for a whole batch:
-// see retry.cuh.  Synchronises `st` once (the host has to learn how many QPs go round again).
+// see retry.cuh.  Asynchronous like the plain call: the second launch reads the number of QPs that go
+// round again from device memory.
 int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   if (!d || !(d->flags & MGQP_FLAG_RETRY_WITHOUT_CI)) return solve_device_once(d, device, st);
   mgqp_batch first = *d;
@@ -431,12 +444,19 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   CU(cudaMemsetAsync(count, 0, 8, st));
   retry_mark_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d->f, d->status, B, idx, count);
   g_launches.fetch_add(1);
-  unsigned long long cnt = 0;
-  CU(cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  if (cnt == 0) {
-    CU(cudaFreeAsync(idx, st));
-    return MGQP_OK;
+  // Size the compact second batch for the worst case (every QP goes round again) and let the kernels read
+  // the real count from the device, so that the call stays asynchronous; only when that workspace would be
+  // unreasonably large does the host wait for the count.
+  const size_t per_qp = (size_t)(n * n + n + n * p + p + n + 1) * 8 + (size_t)(3 + p) * 4;
+  unsigned long long cnt = (unsigned long long)B;
+  const bool on_device_count = per_qp * (size_t)B <= ((size_t)2 << 30);
+  if (!on_device_count) {
+    CU(cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (cnt == 0) {
+      CU(cudaFreeAsync(idx, st));
+      return MGQP_OK;
+    }
   }
   // compact second batch: G' g0 CE ce0 | x f | status iq A iters
   const long long c = (long long)cnt;
@@ -473,7 +493,7 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   second.x = x2; second.f = f2; second.status = st2; second.iq = iq2; second.A = p ? A2 : nullptr; second.iters = it2;
   second.max_iter = d->max_iter;
   second.flags = first.flags;
-  rc = solve_device_once(&second, device, st);
+  rc = solve_device_once(&second, device, st, count);
   if (!rc) {
     RetryScatter sc;
     sc.n = (int)n; sc.pm = (int)(p + m); sc.p = (int)p;
