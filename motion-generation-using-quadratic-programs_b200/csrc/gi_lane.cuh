@@ -98,15 +98,16 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
 enum { LN_ONE = 0x01, LN_DENSE = 0x02, LN_ROW = 0x38, LN_ROW_SHIFT = 3, LN_EXCL = 0x40, LN_ACT = 0x80 };
 
 MGQP_DEV double ln_distance(double a, double b) {
+  // One division and one square root whichever argument is the larger: the two branches of the reference
+  // are the same formula with the arguments swapped, and lanes that disagree on the comparison would
+  // otherwise run both.  Equal magnitudes -- and the reference's fall-through for unordered ones -- return
+  // a1*sqrt(2) up front: sparse problems (G = I, bound constraints) meet distance(0, 0) all the time.
   const double a1 = d_abs(a), b1 = d_abs(b);
-  if (a1 > b1) {
-    const double t = d_div(b1, a1);
-    return d_mul(a1, d_sqrt(d_add(1.0, d_mul(t, t))));
-  } else if (b1 > a1) {
-    const double t = d_div(a1, b1);
-    return d_mul(b1, d_sqrt(d_add(1.0, d_mul(t, t))));
-  }
-  return d_mul(a1, d_sqrt(2.0));
+  const bool agt = a1 > b1;
+  if (!agt && !(b1 > a1)) return d_mul(a1, d_sqrt(2.0));
+  const double hi = agt ? a1 : b1, lo = agt ? b1 : a1;
+  const double t = d_div(lo, hi);
+  return d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t))));
 }
 
 // (c, s) -> normalised rotation coefficients exactly as add_constraint / delete_constraint derive

@@ -5,9 +5,11 @@ usage: ncu_by_phase.py <src.csv> <cubin> <kernel substring> <file> name:lo-hi [n
 import csv, re, subprocess, sys
 from collections import defaultdict
 
-src_csv, cubin, kname, fname = sys.argv[1:5]
+INNER = "--inner" in sys.argv   # attribute to the INNERMOST line of `file` on the inline chain (lambda bodies) instead
+argv = [a for a in sys.argv if a != "--inner"]
+src_csv, cubin, kname, fname = argv[1:5]
 ranges = []
-for a in sys.argv[5:]:
+for a in argv[5:]:
     nm, r = a.split(":")
     lo, hi = r.split("-")
     ranges.append((nm, int(lo), int(hi)))
@@ -34,7 +36,7 @@ for ln in dis:
         fresh = False
         outer = [c for c in chain if c[0] == fname]
         inner = chain[0] if chain else ("?", 0)
-        addr2[int(m.group(1), 16)] = (outer[-1][1] if outer else -1, inner, m.group(2).strip())
+        addr2[int(m.group(1), 16)] = ((outer[0][1] if INNER else outer[-1][1]) if outer else -1, inner, m.group(2).strip())
 rows = list(csv.reader(open(src_csv)))
 hi_ = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi_]
