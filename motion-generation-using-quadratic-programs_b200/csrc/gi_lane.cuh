@@ -106,7 +106,7 @@ MGQP_DEV double ln_distance(double a, double b) {
   const bool agt = a1 > b1;
   if (!agt && !(b1 > a1)) return d_mul(a1, d_sqrt(2.0));
   const double hi = agt ? a1 : b1, lo = agt ? b1 : a1;
-  const double t = d_div(lo, hi);
+  const double t = d_div(lo, hi);  // (the zero-numerator shortcut d_div_z costs this kernel 1.3 %: its d is dense)
   return d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t))));
 }
 

@@ -91,7 +91,7 @@ MGQP_DEV double gi_distance(double a, double b) {
   const bool agt = a1 > b1;
   if (!agt && !(b1 > a1)) return d_mul(a1, d_sqrt(2.0));
   const double hi = agt ? a1 : b1, lo = agt ? b1 : a1;
-  const double t = d_div(lo, hi);
+  const double t = d_div_z(lo, hi);  // distance(0, h) is the common case on sparse problems
   return d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t))));
 }
 
@@ -236,7 +236,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     double acc = in_n ? sg0[li] : 0.0, yv = 0.0;
     MGQP_UNROLL1
     for (int j = 0; j < n; j++) {
-      const double q = d_div(acc, sG[j * n + j]);
+      const double q = d_div_z(acc, sG[j * n + j]);  // g0 = 0 in the reference's own caller (src/mgqp.cpp:706)
       const double yj = wp_shfl(q, j, GW);
       if (li == j) yv = yj;
       if (in_n && li > j) acc = msub<FMA>(acc, sG[li * n + j], yj);
@@ -248,7 +248,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       double a = sd[i];
       MGQP_UNROLL1
       for (int j = i + 1; j < n; j++) a = msub<FMA>(a, sG[i * n + j], sx[j]);
-      a = d_div(a, sG[i * n + i]);
+      a = d_div_z(a, sG[i * n + i]);
       sx[i] = a;  // every lane of the group stores the same value
       if (li == i) xv = -a;
     }
@@ -293,7 +293,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       double sum = 0.0;
       MGQP_UNROLL1
       for (int j = i + 1; j < iq; j++) sum = mad<FMA>(sR[i * ldR + j], sr[j], sum);
-      const double ri = d_div(d_sub(sd[i], sum), sR[i * ldR + i]);
+      const double ri = d_div_z(d_sub(sd[i], sum), sR[i * ldR + i]);
       sr[i] = ri;  // same value from every lane of the group
       if (li == i) rv = ri;
     }
@@ -327,11 +327,11 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     // reference's sign normalisation; the incoming d[j] is what rotation j+1 leaves behind.
     const bool myrot = li >= jlo && li <= n - 1 && !((skipm >> li) & 1u);
     const double dprev = (li > 0 && in_n) ? sd[li - 1] : 0.0;
-    double c = d_div(dprev, hreg);
+    double c = d_div_z(dprev, hreg);
     const double dnew = ((skipm >> li) & 1u) ? dprev : ((c < 0.0) ? -hreg : hreg);  // new d[li-1]
     const double dnext = wp_shfl_down(dnew, 1, GW);
     const double din = (li == n - 1) ? sd[n - 1] : dnext;
-    double sn = d_div(din, hreg);
+    double sn = d_div_z(din, hreg);
     if (c < 0.0) {
       c = -c;
       sn = -sn;
@@ -339,7 +339,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (myrot) {
       sgc[li] = c;
       sgs[li] = sn;
-      sgx[li] = d_div(sn, d_add(1.0, c));
+      sgx[li] = d_div_z(sn, d_add(1.0, c));
     }
     const double dl_rot = wp_shfl(dnew, jlo & (GW - 1), GW);
     const double dlast = (jlo <= n - 1) ? dl_rot : sd[iq < n ? iq : 0];

@@ -186,6 +186,7 @@ MGQP_DEV double d_mul(double a, double b) { return a * b; }
 MGQP_DEV double d_add(double a, double b) { return a + b; }
 MGQP_DEV double d_sub(double a, double b) { return a - b; }
 MGQP_DEV double d_div(double a, double b) { return a / b; }
+MGQP_DEV double d_div_z(double a, double b) { return a / b; }
 MGQP_DEV double d_sqrt(double a) { return sqrt(a); }
 MGQP_DEV double d_fma(double a, double b, double c) { return fma(a, b, c); }
 MGQP_DEV double d_abs(double a) { return fabs(a); }
