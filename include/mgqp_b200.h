@@ -146,6 +146,11 @@ int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const doubl
 int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI,
                             double* val, int64_t sv, uint8_t* row, int64_t sr, int threads);
 
+/* Host threads the packer uses by default: MGQP_HOST_THREADS, else the cores this process may run on.
+ * The host-buffer entry points pack CI only when these threads can outrun what the packing saves on
+ * the link (one rank per GPU on a 32-core box leaves 4 threads per GPU: dense transport wins there). */
+int mgqp_host_pack_threads(void);
+
 /* Bytes the last host-buffer call of the calling thread moved over the host<->device link. */
 void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h);
 

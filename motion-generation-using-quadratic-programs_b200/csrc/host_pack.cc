@@ -191,6 +191,8 @@ Pool& pool() {
 
 }  // namespace
 
+extern "C" int mgqp_host_pack_threads(void) { return default_threads(); }
+
 extern "C" int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI, double* val,
                                        int64_t sv, uint8_t* row, int64_t sr, int threads) {
   if (n < 1 || n > 255 || m < 0 || m > 64 || count < 0) return 0;

@@ -655,9 +655,20 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     carve_bufs(bufs[i], h, chunk, static_cast<char*>(ctx->arena[i]));
   }
   // CI goes up in column-compressed form where the lane kernel serves the shape (see run_chunk)
-  const bool pack = !(h->flags & (MGQP_FLAG_NO_HOST_PACK | MGQP_FLAG_CTA_KERNEL)) && !h->CI_val && h->m > 0 &&
-                    h->m <= 64 && h->sCI != 0 &&
-                    (make_lane_plan(h->n, h->p, h->m, ctx->smem_optin).ok || make_plan(h->n, h->p, h->m, ctx->smem_optin).gw > 0);
+  bool pack = !(h->flags & (MGQP_FLAG_NO_HOST_PACK | MGQP_FLAG_CTA_KERNEL)) && !h->CI_val && h->m > 0 &&
+              h->m <= 64 && h->sCI != 0 &&
+              (make_lane_plan(h->n, h->p, h->m, ctx->smem_optin).ok || make_plan(h->n, h->p, h->m, ctx->smem_optin).gw > 0);
+  if (pack) {
+    // Worth it only if the host threads can read CI faster than the link would have carried it.  Measured
+    // (profiles/r01_notes.md): ~6 GB/s of CI per packing thread, ~50 GB/s over PCIe; 16 threads per GPU
+    // double the C2 rate, 8 still gain 28 %, 4 lose 20 % against dense transport.
+    const double n = h->n, p = h->p, m = h->m;
+    const double rest = 8.0 * (n * n + n + n * p + p + m) + 8.0 * (n + 1) + 4.0;
+    const double link = 50e9, per_thread = 6e9;
+    const double t_dense = (rest + 8.0 * n * m) / link;
+    const double t_link = (rest + 9.0 * m) / link, t_cpu = 8.0 * n * m / (per_thread * mgqp_host_pack_threads());
+    pack = (t_link > t_cpu ? t_link : t_cpu) < 0.8 * t_dense;
+  }
   if (pack) {
     const size_t vbytes = ((size_t)chunk * h->m * 8 + 255) & ~(size_t)255;
     const size_t pneed = vbytes + (size_t)chunk * packed_row_stride(h->m);

@@ -20,6 +20,9 @@ def gpu():
     import torch
     import __graft_entry__ as g
     g.build()
+    # the host pipeline packs CI only where it has the threads to outrun the link; the transport tests below
+    # check byte counts of the packed form, so ask for it whatever box this runs on
+    os.environ.setdefault("MGQP_HOST_THREADS", "16")
     import mgqp_b200
     assert torch.cuda.is_available(), "these tests need a B200"
     mgqp_b200.lib()
