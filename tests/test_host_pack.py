@@ -65,3 +65,17 @@ def test_empty_and_degenerate_sizes(lib):
     val, row = lib.pack_bound_columns(np.zeros((5, 7, 0)))
     assert val.shape == (5, 0)
     assert lib.pack_bound_columns(np.zeros((3, 7, 65))) is None      # beyond the lane kernel's m <= 64
+
+
+def test_pack_thread_count_follows_the_environment(lib, monkeypatch):
+    """The host pipeline decides between packed and dense transport from this number (one rank per GPU
+    shares the box's cores: bench.py hands every rank cores / local world size)."""
+    L = lib.lib()
+    L.mgqp_host_pack_threads.restype = int
+    monkeypatch.setenv("MGQP_HOST_THREADS", "5")
+    assert L.mgqp_host_pack_threads() == 5
+    monkeypatch.setenv("MGQP_HOST_THREADS", "1000")
+    assert L.mgqp_host_pack_threads() == 64
+    monkeypatch.delenv("MGQP_HOST_THREADS")
+    import os
+    assert 1 <= L.mgqp_host_pack_threads() <= max(1, len(os.sched_getaffinity(0)))
