@@ -153,6 +153,45 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     return acc;
   };
 
+  // two / three such sums in one pass (the Givens-coefficient rows double as scratch: they are only
+  // live inside add_constraint): one pair of barriers and one loop instead of three, each sum still
+  // accumulated in ascending index order
+  auto osum2 = [&](double v0, double v1, double& r0, double& r1) {
+    if (in_n) {
+      sred[li] = v0;
+      sgc[li] = v1;
+    }
+    wp_sync();
+    double a0 = 0.0, a1 = 0.0;
+    MGQP_UNROLL1
+    for (int i = 0; i < n; i++) {
+      a0 = d_add(a0, sred[i]);
+      a1 = d_add(a1, sgc[i]);
+    }
+    wp_sync();
+    r0 = a0;
+    r1 = a1;
+  };
+  auto osum3 = [&](double v0, double v1, double v2, double& r0, double& r1, double& r2) {
+    if (in_n) {
+      sred[li] = v0;
+      sgc[li] = v1;
+      sgs[li] = v2;
+    }
+    wp_sync();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    MGQP_UNROLL1
+    for (int i = 0; i < n; i++) {
+      a0 = d_add(a0, sred[i]);
+      a1 = d_add(a1, sgc[i]);
+      a2 = d_add(a2, sgs[i]);
+    }
+    wp_sync();
+    r0 = a0;
+    r1 = a1;
+    r2 = a2;
+  };
+
   int status = ST_OK;
   bool done = false;
   double f = 0.0;
@@ -277,15 +316,18 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     dv = 0.0;
     npv = in_n ? npp[li * nps] : 0.0;
     if (in_n) {
-      MGQP_UNROLL1
-      for (int j = 0; j < n; j++) dv = mad<FMA>(sJ[j * ldJ + li], npp[j * nps], dv);
+      const double* pj = sJ + li;
+      const double* pn = npp;
+      MGQP_UNROLL2
+      for (int j = 0; j < n; j++, pj += ldJ, pn += nps) dv = mad<FMA>(*pj, *pn, dv);
     }
     if (in_n) sd[li] = dv;
     wp_sync();
     zv = 0.0;
     if (in_n) {
-      MGQP_UNROLL1
-      for (int j = iq; j < n; j++) zv = mad<FMA>(sJ[li * ldJ + j], sd[j], zv);
+      const double* pj = sJ + li * ldJ;
+      MGQP_UNROLL2
+      for (int j = iq; j < n; j++) zv = mad<FMA>(pj[j], sd[j], zv);
     }
     rv = 0.0;
     MGQP_UNROLL1
@@ -442,9 +484,8 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   MGQP_UNROLL1
   for (int e = 0; e < p; e++) {
     direction(sCE + e, p);
-    const double zz = osum(d_mul(zv, zv));
-    const double npx = osum(d_mul(npv, xv));
-    const double znp = osum(d_mul(zv, npv));
+    double zz, npx, znp;
+    osum3(d_mul(zv, zv), d_mul(npv, xv), d_mul(zv, npv), zz, npx, znp);
     double t2 = 0.0;
     if (d_abs(zz) > MGQP_EPS) t2 = d_div(d_sub(-npx, sce0[e]), znp);
     if (!done) {
@@ -585,8 +626,8 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     const double t1 = ratio;
     const int l_src = wp_shfl(Av, (lk == NONE) ? 0 : lk, GW);
     const int l = (lk == NONE) ? 0 : l_src;
-    const double zz = osum(d_mul(zv, zv));
-    const double znp = osum(d_mul(zv, npv));
+    double zz, znp;
+    osum2(d_mul(zv, zv), d_mul(zv, npv), zz, znp);
     double t2;
     if (d_abs(zz) > MGQP_EPS) {
       t2 = d_div(-s_ip, znp);

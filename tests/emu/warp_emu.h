@@ -23,6 +23,7 @@
 #define MGQP_DEV static inline
 #define MGQP_DEV_NOINLINE static inline
 #define MGQP_UNROLL1
+#define MGQP_UNROLL2
 #define MGQP_HD
 #define MGQP_HOST
 #define MGQP_FULL 0xffffffffu
