@@ -163,7 +163,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     }
     wp_sync();
     double a0 = 0.0, a1 = 0.0;
-    MGQP_UNROLL1
+    MGQP_UNROLL2
     for (int i = 0; i < n; i++) {
       a0 = d_add(a0, sred[i]);
       a1 = d_add(a1, sgc[i]);
@@ -180,7 +180,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     }
     wp_sync();
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    MGQP_UNROLL1
+    MGQP_UNROLL2
     for (int i = 0; i < n; i++) {
       a0 = d_add(a0, sred[i]);
       a1 = d_add(a1, sgc[i]);
@@ -227,8 +227,10 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     double sum = 0.0;
     if (act) {
       sum = sG[i * n + li];
-      MGQP_UNROLL1
-      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sG[i * n + k], sG[li * n + k]);
+      const double* gi = sG + i * n;
+      const double* gl = sG + li * n;
+      MGQP_UNROLL2
+      for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, gi[k], gl[k]);
     }
     const double piv = wp_shfl(sum, i, GW);
     if (!done && piv <= 0.0) {
@@ -257,8 +259,10 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     MGQP_UNROLL1
     for (int r = 0; r < n; r++) {
       double acc = (r == li) ? 1.0 : 0.0;
-      MGQP_UNROLL1
-      for (int j = 0; j < r; j++) acc = msub<FMA>(acc, sG[r * n + j], sJ[li * ldJ + j]);
+      const double* grow = sG + r * n;
+      const double* jrow = sJ + li * ldJ;
+      MGQP_UNROLL2
+      for (int j = 0; j < r; j++) acc = msub<FMA>(acc, grow[j], jrow[j]);
       sJ[li * ldJ + r] = d_div(acc, sG[r * n + r]);
     }
   }
@@ -285,8 +289,9 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     MGQP_UNROLL1
     for (int i = n - 1; i >= 0; i--) {
       double a = sd[i];
-      MGQP_UNROLL1
-      for (int j = i + 1; j < n; j++) a = msub<FMA>(a, sG[i * n + j], sx[j]);
+      const double* grow = sG + i * n;
+      MGQP_UNROLL2
+      for (int j = i + 1; j < n; j++) a = msub<FMA>(a, grow[j], sx[j]);
       a = d_div_z(a, sG[i * n + i]);
       sx[i] = a;  // every lane of the group stores the same value
       if (li == i) xv = -a;
@@ -333,8 +338,9 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     MGQP_UNROLL1
     for (int i = iq - 1; i >= 0; i--) {
       double sum = 0.0;
-      MGQP_UNROLL1
-      for (int j = i + 1; j < iq; j++) sum = mad<FMA>(sR[i * ldR + j], sr[j], sum);
+      const double* ri_row = sR + i * ldR;
+      MGQP_UNROLL2
+      for (int j = i + 1; j < iq; j++) sum = mad<FMA>(ri_row[j], sr[j], sum);
       const double ri = d_div_z(d_sub(sd[i], sum), sR[i * ldR + i]);
       sr[i] = ri;  // same value from every lane of the group
       if (li == i) rv = ri;
@@ -388,20 +394,21 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     wp_sync();
     // (3) lane k streams row k of J right to left through all rotations; no synchronisation needed
     if (in_n) {
-      double t2 = sJ[li * ldJ + n - 1];
-      MGQP_UNROLL1
+      double* jrow = sJ + li * ldJ;
+      double t2 = jrow[n - 1];
+      MGQP_UNROLL2
       for (int j = n - 1; j >= jlo; j--) {
-        const double t1 = sJ[li * ldJ + j - 1];
+        const double t1 = jrow[j - 1];
         if (!((skipm >> j) & 1u)) {
           const double n1 = d_add(d_mul(t1, sgc[j]), d_mul(t2, sgs[j]));
-          sJ[li * ldJ + j] = d_sub(d_mul(sgx[j], d_add(t1, n1)), t2);
+          jrow[j] = d_sub(d_mul(sgx[j], d_add(t1, n1)), t2);
           t2 = n1;
         } else {
-          sJ[li * ldJ + j] = t2;
+          jrow[j] = t2;
           t2 = t1;
         }
       }
-      if (jlo <= n - 1) sJ[li * ldJ + jlo - 1] = t2;
+      if (jlo <= n - 1) jrow[jlo - 1] = t2;
     }
     bool ok = true;
     if (doit) {
@@ -537,8 +544,9 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
         const int i = li + (k << LOGG);
         if (i < m) {
           double sum = 0.0;
-          MGQP_UNROLL1
-          for (int j = 0; j < n; j++) sum = mad<FMA>(sCI[j * m + i], sx[j], sum);
+          const double* pc = sCI + i;
+          MGQP_UNROLL2
+          for (int j = 0; j < n; j++, pc += m) sum = mad<FMA>(*pc, sx[j], sum);
           sum = d_add(sum, sci0[i]);
           if (sum < 0.0) psi = d_add(psi, sum);
           if (sum < best && !((act_mask >> k) & 1u) && ((excl_mask >> k) & 1u)) {
