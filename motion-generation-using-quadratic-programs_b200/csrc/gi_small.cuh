@@ -26,6 +26,10 @@
 #pragma once
 #include "warp_prims.cuh"
 
+#ifndef MGQP_UNROLL_HOT
+#define MGQP_UNROLL_HOT MGQP_UNROLL4  // the four hottest loops (d, z, scan column, Givens row streaming); 2 -> 4: +1 %
+#endif
+
 namespace mgqp {
 
 #define MGQP_EPS 2.220446049250313e-16 /* std::numeric_limits<double>::epsilon() */
@@ -323,7 +327,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (in_n) {
       const double* pj = sJ + li;
       const double* pn = npp;
-      MGQP_UNROLL2
+      MGQP_UNROLL_HOT
       for (int j = 0; j < n; j++, pj += ldJ, pn += nps) dv = mad<FMA>(*pj, *pn, dv);
     }
     if (in_n) sd[li] = dv;
@@ -331,7 +335,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     zv = 0.0;
     if (in_n) {
       const double* pj = sJ + li * ldJ;
-      MGQP_UNROLL2
+      MGQP_UNROLL_HOT
       for (int j = iq; j < n; j++) zv = mad<FMA>(pj[j], sd[j], zv);
     }
     rv = 0.0;
@@ -396,7 +400,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (in_n) {
       double* jrow = sJ + li * ldJ;
       double t2 = jrow[n - 1];
-      MGQP_UNROLL2
+      MGQP_UNROLL_HOT
       for (int j = n - 1; j >= jlo; j--) {
         const double t1 = jrow[j - 1];
         if (!((skipm >> j) & 1u)) {
@@ -545,7 +549,7 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
         if (i < m) {
           double sum = 0.0;
           const double* pc = sCI + i;
-          MGQP_UNROLL2
+          MGQP_UNROLL_HOT
           for (int j = 0; j < n; j++, pc += m) sum = mad<FMA>(*pc, sx[j], sum);
           sum = d_add(sum, sci0[i]);
           if (sum < 0.0) psi = d_add(psi, sum);

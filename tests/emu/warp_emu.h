@@ -24,6 +24,9 @@
 #define MGQP_DEV_NOINLINE static inline
 #define MGQP_UNROLL1
 #define MGQP_UNROLL2
+#ifndef MGQP_UNROLL4
+#define MGQP_UNROLL4
+#endif
 #define MGQP_HD
 #define MGQP_HOST
 #define MGQP_FULL 0xffffffffu
