@@ -151,6 +151,12 @@ int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* C
  * the link (one rank per GPU on a 32-core box leaves 4 threads per GPU: dense transport wins there). */
 int mgqp_host_pack_threads(void);
 
+/* 1 iff all `count` blocks of `size` doubles (element stride `stride`) equal the first one bit for bit.
+ * The host-buffer entry points use it on G and g0, chunk by chunk: the reference's own caller passes
+ * G = I and g0 = 0 for every QP (src/mgqp.cpp:672, :706), and such a field is then uploaded once per
+ * chunk (device-side stride 0) instead of once per QP. */
+int mgqp_blocks_all_equal(const double* base, int64_t stride, int64_t size, int64_t count, int threads);
+
 /* Bytes the last host-buffer call of the calling thread moved over the host<->device link. */
 void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h);
 

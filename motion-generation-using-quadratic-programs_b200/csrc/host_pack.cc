@@ -193,6 +193,35 @@ Pool& pool() {
 
 extern "C" int mgqp_host_pack_threads(void) { return default_threads(); }
 
+// 1 iff every one of `count` blocks of `size` doubles (element stride `stride` between blocks) is bit for
+// bit the first one: the reference's own caller passes G = I and g0 = 0 for every QP (src/mgqp.cpp:672,
+// :706), and such a field can cross the link once per chunk instead of once per QP.
+extern "C" int mgqp_blocks_all_equal(const double* base, int64_t stride, int64_t size, int64_t count, int threads) {
+  if (count <= 1 || size <= 0) return 1;
+  if (threads <= 0) threads = default_threads();
+  const int64_t block = 4096;
+  const int64_t blocks = (count + block - 1) / block;
+  if (threads > blocks) threads = (int)blocks;
+  std::atomic<int64_t> next(0);
+  std::atomic<int> differ(0);
+  const size_t bytes = (size_t)size * 8;
+  const std::function<void()> work = [&]() {
+    for (;;) {
+      const int64_t b = next.fetch_add(1);
+      if (b >= blocks || differ.load(std::memory_order_relaxed)) break;
+      const int64_t q1 = (b + 1) * block < count ? (b + 1) * block : count;
+      for (int64_t q = b * block; q < q1; q++)
+        if (memcmp(base, base + q * stride, bytes) != 0) {
+          differ.store(1, std::memory_order_relaxed);
+          break;
+        }
+    }
+  };
+  if (threads <= 1) work();
+  else pool().run(work, threads - 1);
+  return differ.load() ? 0 : 1;
+}
+
 extern "C" int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI, double* val,
                                        int64_t sv, uint8_t* row, int64_t sr, int threads) {
   if (n < 1 || n > 255 || m < 0 || m > 64 || count < 0) return 0;

@@ -593,6 +593,11 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
       CU(cudaMemcpyAsync(f.dst, f.src, (size_t)f.size * 8, cudaMemcpyHostToDevice, st));
       *f.dstride = 0;
       g_h2d_bytes += f.size * 8;
+    } else if (k < 2 && pack && cnt > 1 && mgqp_blocks_all_equal(f.src + q0 * f.stride, f.stride, f.size, cnt, 0)) {
+      // G / g0 identical in every QP of the chunk (the reference's caller: G = I, g0 = 0): one instance
+      CU(cudaMemcpyAsync(f.dst, f.src + q0 * f.stride, (size_t)f.size * 8, cudaMemcpyHostToDevice, st));
+      *f.dstride = 0;
+      g_h2d_bytes += f.size * 8;
     } else if (f.stride == f.size) {
       CU(cudaMemcpyAsync(f.dst, f.src + q0 * f.stride, (size_t)(cnt * f.size) * 8, cudaMemcpyHostToDevice, st));
       *f.dstride = f.size;

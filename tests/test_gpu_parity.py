@@ -265,7 +265,15 @@ def test_column_compressed_device_input(gpu, restatement):
         r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=1024)
         up, _ = gpu.last_transfer_bytes()
         assert_bit_identical(r._asdict(), ref, name + " host")
-        assert up == 8 * B * (b.n * b.n + b.n + b.n * b.p + b.p + 2 * b.m) + B * ((b.m + 15) // 16 * 16)
+        # G = I and g0 = 0 in every QP (the reference's own caller): one instance per chunk, not per QP
+        chunks = [min(1024, B - q) for q in range(0, B, 1024)]
+        assert up == sum(8 * (b.n * b.n + b.n) + c * (8 * (b.n * b.p + b.p + 2 * b.m) + (b.m + 15) // 16 * 16) for c in chunks)
+        b.G[B // 2, 3, 3] = 1.25    # one QP with its own G: that chunk ships G per QP again, same answers
+        ref = _oracle(restatement, b)
+        r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=1024)
+        up2, _ = gpu.last_transfer_bytes()
+        assert_bit_identical(r._asdict(), ref, name + " host, one odd G")
+        assert up2 == up + 8 * b.n * b.n * (chunks[(B // 2) // 1024] - 1)
     b = workloads.make_random(8, 40, 2, 10, seed=1)  # n = 40: CTA-per-QP kernel, no compressed form there
     val = torch.zeros((8, b.m), dtype=torch.float64, device="cuda")
     row = torch.zeros((8, b.m), dtype=torch.uint8, device="cuda")

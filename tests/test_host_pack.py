@@ -79,3 +79,21 @@ def test_pack_thread_count_follows_the_environment(lib, monkeypatch):
     monkeypatch.delenv("MGQP_HOST_THREADS")
     import os
     assert 1 <= L.mgqp_host_pack_threads() <= max(1, len(os.sched_getaffinity(0)))
+
+
+def test_blocks_all_equal(lib):
+    import ctypes as C
+    L = lib.lib()
+    L.mgqp_blocks_all_equal.restype = C.c_int
+    L.mgqp_blocks_all_equal.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]
+    b = workloads.make("S2", 20000)       # the shipped shape: G = I, g0 = 0 in every QP
+    for th in (1, 0):
+        assert L.mgqp_blocks_all_equal(b.G.ctypes.data, 196, 196, b.batch, th) == 1
+        assert L.mgqp_blocks_all_equal(b.g0.ctypes.data, 14, 14, b.batch, th) == 1
+    b.G[19999, 13, 13] = np.nextafter(1.0, 2.0)
+    assert L.mgqp_blocks_all_equal(b.G.ctypes.data, 196, 196, b.batch, 0) == 0
+    b.g0[7, 0] = -0.0                       # bitwise, not numeric, equality
+    assert L.mgqp_blocks_all_equal(b.g0.ctypes.data, 14, 14, b.batch, 0) == 0
+    c = workloads.make("C2", 5000)
+    assert L.mgqp_blocks_all_equal(c.G.ctypes.data, 49, 49, c.batch, 0) == 0
+    assert L.mgqp_blocks_all_equal(c.G.ctypes.data, 49, 49, 1, 0) == 1
