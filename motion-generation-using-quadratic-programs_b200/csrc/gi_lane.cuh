@@ -336,9 +336,10 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll 1
     for (int k = i - 1; k >= 0; k--) {
       const double lik = Ls[i * N + k];
+      // (all N columns, not only j >= i: the sums of the columns left of the diagonal are never used,
+      // and a select per column costs more than the wasted multiply-subtract)
 #pragma unroll
-      for (int j = 0; j < N; j++)
-        if (j >= i) sum[j] = msub<FMA>(sum[j], lik, Ls[j * N + k]);
+      for (int j = 0; j < N; j++) sum[j] = msub<FMA>(sum[j], lik, Ls[j * N + k]);
     }
     double piv = 0.0;
 #pragma unroll
@@ -395,7 +396,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll 1
     for (int i = 1; i < N; i++) {
       double a = g0s[i];
-#pragma unroll 1
+#pragma unroll 2
       for (int j = 0; j < i; j++) a = msub<FMA>(a, Ls[i * N + j], ys[j]);
       ys[i] = d_div(a, Ls[i * N + i]);
     }
@@ -403,7 +404,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 #pragma unroll 1
     for (int i = N - 2; i >= 0; i--) {
       double a = ys[i];
-#pragma unroll 1
+#pragma unroll 2
       for (int j = i + 1; j < N; j++) a = msub<FMA>(a, Ls[i * N + j], xs[j]);
       xs[i] = d_div(a, Ls[i * N + i]);
     }
