@@ -27,9 +27,16 @@
 #ifdef MGQP_EMULATE
 #define MGQP_UNROLL8
 #define MGQP_UNROLL4
+#define MGQP_UNROLL_SETUP
 #else
 #define MGQP_UNROLL8 _Pragma("unroll 8")
 #define MGQP_UNROLL4 _Pragma("unroll 4")
+#ifndef MGQP_SETUP_DEPTH
+#define MGQP_SETUP_DEPTH 8
+#endif
+#define MGQP_PRAGMA_(x) _Pragma(#x)
+#define MGQP_PRAGMA(x) MGQP_PRAGMA_(x)
+#define MGQP_UNROLL_SETUP MGQP_PRAGMA(unroll MGQP_SETUP_DEPTH)
 #endif
 
 namespace mgqp {
@@ -237,7 +244,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     MGQP_UNROLL1
     for (int j = i + tid; j < n; j += T) {
       double sum = Gc[(size_t)i * n + j];
-      MGQP_UNROLL8
+      MGQP_UNROLL_SETUP
       // L[j][k] is read as its mirror image Gc[k][j] (written when row k was finished): same bits,
       // and consecutive threads (j) touch consecutive addresses
       for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, sz[k], Gc[(size_t)k * n + j]);
@@ -282,18 +289,28 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     const bool finite_L = sredi[0] == 0;
     blk_sync();
     MGQP_UNROLL1
-    for (int i = tid; i < n; i += T) {
+    for (int ib = 0; ib < n; ib += T) {
+      const int i = ib + tid;
+      const bool have = i < n;
       double* Ji = J + i;  // row i of J = column i of the transposed store: element r at Ji[r * n]
-      const int r0 = finite_L ? i : 0;
+      // Every lane of a warp runs the same (r, j) ranges, starting at the warp's first row iw: lane i's
+      // loads J[j][i] then sit next to its neighbours' (one 256-byte segment per warp), whereas a start
+      // at each lane's own diagonal put every lane on a different row j (stride n + 1: one 32-byte
+      // sector per lane).  The extra terms j in [iw, i) multiply stored +0.0 entries: no effect.
+      const int iw = finite_L ? (ib + (tid & ~31)) : 0;
+      if (have && finite_L) {
+        MGQP_UNROLL1
+        for (int r = 0; r < i; r++) Ji[(size_t)r * n] = 0.0;
+      }
       MGQP_UNROLL1
-      for (int r = 0; r < r0; r++) Ji[(size_t)r * n] = 0.0;
-      MGQP_UNROLL1
-      for (int r = r0; r < n; r++) {
-        double acc = (r == i) ? 1.0 : 0.0;
-        const double* Lr = Gc + (size_t)r * n;
-        MGQP_UNROLL8
-        for (int j = r0; j < r; j++) acc = msub<FMA>(acc, Lr[j], Ji[(size_t)j * n]);
-        Ji[(size_t)r * n] = d_div(acc, Lr[r]);
+      for (int r = iw; r < n; r++) {
+        if (have && (r >= i || !finite_L)) {
+          double acc = (r == i) ? 1.0 : 0.0;
+          const double* Lr = Gc + (size_t)r * n;
+          MGQP_UNROLL_SETUP
+          for (int j = iw; j < r; j++) acc = msub<FMA>(acc, Lr[j], Ji[(size_t)j * n]);
+          Ji[(size_t)r * n] = d_div(acc, Lr[r]);
+        }
       }
     }
     blk_sync();
