@@ -330,12 +330,21 @@ def _retry_policy_expected(restatement, b, ref):
     return exp, again
 
 
-@pytest.mark.parametrize("name,B,flags", [("C5", 6007, 0), ("C5", 6007, 8), ("S2", 3001, 0)])
+@pytest.mark.parametrize("name,B,flags", [("C5", 6007, 0), ("C5", 6007, 8), ("S2", 3001, 0), ("C3", 2001, 0),
+                                          ("R40", 257, 0)])
 def test_infeasible_retry_policy_of_the_reference_adapter(gpu, restatement, name, B, flags):
-    b = workloads.make(name, B)
+    if name == "R40":                     # n = 40: CTA-per-QP kernel; the gather's Cholesky spans two lane strips
+        b = workloads.make_random(B, 40, 2, 10, seed=40)
+        b.CI[::3, :, 0] = 0.0; b.CI[::3, 0, 0] = 1.0; b.ci0[::3, 0] = -1.0     #  x0 >= 1
+        b.CI[::3, :, 1] = 0.0; b.CI[::3, 0, 1] = -1.0; b.ci0[::3, 1] = -1.0    # -x0 >= 1
+    else:
+        b = workloads.make(name, B)
     if name == "S2":                      # the shipped shape is always feasible: contradict a bound pair
         b.ci0[::9, 3] = -7.0
         b.ci0[::9, 3 + 14] = -7.0
+    if name == "C3":                      # general G, n = 14, p = 7: contradict the first joint's bound pair
+        b.CI[::5, :, 0] = 0.0; b.CI[::5, 0, 0] = 1.0; b.ci0[::5, 0] = -3.0
+        b.CI[::5, :, 1] = 0.0; b.CI[::5, 0, 1] = -1.0; b.ci0[::5, 1] = -3.0
     b.ce0[5::97, 0] = np.nan              # NaN cost both times: the command is zeroed (status 17)
     ref = _oracle(restatement, b)
     exp, again = _retry_policy_expected(restatement, b, ref)
