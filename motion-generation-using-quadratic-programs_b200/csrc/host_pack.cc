@@ -24,18 +24,17 @@
 
 namespace {
 
-// One QP (m <= 64 here; the lane kernel's limit).  Each row of CI becomes a bit mask of its nonzero
-// entries (+-0.0 are the zeros, NaN counts as nonzero); a column with two nonzeros shows up as a bit
-// common to two rows.  The ~m nonzeros are then scattered into (val, row); an all-zero column gets
-// (+0.0, row 0).  Returns 1 if some column has more than one nonzero.
-inline int scatter_row(uint64_t mask, int j, const double* r, double* val, uint8_t* row) {
+// One QP (m <= 64: a row's nonzero pattern fits one 64-bit mask).  Each row of CI becomes a bit mask of
+// its nonzero entries (+-0.0 are the zeros, NaN counts as nonzero); a column with two nonzeros shows up as
+// a bit common to two rows.  The ~m nonzeros are then scattered into (val, row); an all-zero column gets
+// (+0.0, row 0).  pack_one_* return 1 if some column has more than one nonzero.
+inline void scatter_row(uint64_t mask, int j, const double* r, double* val, uint8_t* row) {
   while (mask) {
     const int i = __builtin_ctzll(mask);
     mask &= mask - 1;
     val[i] = r[i];
     row[i] = (uint8_t)j;
   }
-  return 0;
 }
 
 int pack_one_generic(int n, int m, const double* __restrict__ ci, double* __restrict__ val, uint8_t* __restrict__ row) {
@@ -98,10 +97,6 @@ pack_fn pick_pack() {
 #endif
   return pack_one_generic;
 }
-
-}  // namespace
-
-namespace {
 
 // A small persistent pool: the host pipeline packs one chunk (tens of thousands of QPs, ~2 ms of
 // work) at a time, far too often to create threads for each.  One job at a time; the caller works too.
