@@ -104,3 +104,28 @@ def test_exception_cases_against_shipped_binary(restatement, reference_binary):
             assert ref["message"] == "Error in cholesky decomposition, sum: %g" % got["f"]
         else:
             assert np.array_equal(got["x"], ref["x"])
+
+
+def test_retry_sequence_of_the_adapter_against_the_binary(restatement, reference_binary):
+    """solveNextStep (src/mgqp.cpp:708-735) calls the solver a second time on the SAME G object, which the
+    first call has overwritten with its mirrored Cholesky factor, after dropping the inequalities.  The
+    oracle's restatement of that two-call sequence (what MGQP_FLAG_RETRY_WITHOUT_CI is tested against on
+    the GPU) must match the shipped binary run the same way, bit for bit."""
+    if reference_binary is None:
+        pytest.skip("oracle/_ref not built here")
+    b = workloads.make("C5", 1500)           # general G (not the identity): the re-factorisation matters
+    n, p, m = b.n, b.p, b.m
+    tried = 0
+    for q in range(b.batch):
+        one = reference_binary.solve_one(b.G[q], b.g0[q], b.CE[q], b.ce0[q], b.CI[q], b.ci0[q])
+        if not (np.isposinf(one["f"]) or np.isnan(one["f"])):
+            continue
+        tried += 1
+        mine = restatement.solve_one(b.G[q], b.g0[q], b.CE[q], b.ce0[q], b.CI[q], b.ci0[q])
+        assert np.array_equal(mine["G_factor"], one["G_factor"])     # what the second call gets as G
+        assert not np.array_equal(one["G_factor"], b.G[q])
+        two = reference_binary.solve_one(one["G_factor"], b.g0[q], b.CE[q], b.ce0[q], np.zeros((n, 0)), np.zeros(0))
+        mine2 = restatement.solve_one(mine["G_factor"], b.g0[q], b.CE[q], b.ce0[q], np.zeros((n, 0)), np.zeros(0))
+        assert two["status"] == mine2["status"]
+        assert np.array_equal(two["x"], mine2["x"]) and two["f"] == mine2["f"]
+    assert tried > 100
