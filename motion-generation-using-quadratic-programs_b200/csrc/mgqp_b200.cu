@@ -426,6 +426,15 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const un
   return fast ? launch_small<32, true>(ctx, pl, P, st, gi, 1) : launch_small<32, false>(ctx, pl, P, st, gi, 0);
 }
 
+// stream-ordered allocation released when the scope ends, whichever way it ends
+struct AsyncBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  ~AsyncBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+
 // The reference adapter's policy for an infeasible answer (src/mgqp.cpp:717-735), for a whole batch:
 // see retry.cuh.  Asynchronous like the plain call: the second launch reads the number of QPs that go
 // round again from device memory.
@@ -437,10 +446,11 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   if (rc || d->batch == 0) return rc;
   if (d->n > 1024) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "MGQP_FLAG_RETRY_WITHOUT_CI serves n <= 1024");
   const long long B = d->batch, n = d->n, p = d->p, m = d->m;
-  long long* idx = nullptr;
-  unsigned long long* count = nullptr;
-  CU(cudaMallocAsync(&idx, (size_t)B * 8 + 8, st));
-  count = reinterpret_cast<unsigned long long*>(idx + B);
+  AsyncBuf idx_buf, ws_buf;
+  idx_buf.st = ws_buf.st = st;
+  CU(cudaMallocAsync(&idx_buf.p, (size_t)B * 8 + 8, st));
+  long long* idx = static_cast<long long*>(idx_buf.p);
+  unsigned long long* count = reinterpret_cast<unsigned long long*>(idx + B);
   CU(cudaMemsetAsync(count, 0, 8, st));
   retry_mark_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(d->f, d->status, B, idx, count);
   g_launches.fetch_add(1);
@@ -453,18 +463,14 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   if (!on_device_count) {
     CU(cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (cnt == 0) {
-      CU(cudaFreeAsync(idx, st));
-      return MGQP_OK;
-    }
+    if (cnt == 0) return MGQP_OK;
   }
   // compact second batch: G' g0 CE ce0 | x f | status iq A iters
   const long long c = (long long)cnt;
   const size_t dbl = (size_t)c * (n * n + n + n * p + p + n + 1);
   const size_t ints = (size_t)c * (3 + p);
-  double* ws = nullptr;
-  CU(cudaMallocAsync(&ws, dbl * 8 + ints * 4 + 64, st));
-  double* G2 = ws;
+  CU(cudaMallocAsync(&ws_buf.p, dbl * 8 + ints * 4 + 64, st));
+  double* G2 = static_cast<double*>(ws_buf.p);
   double* g02 = G2 + c * n * n;
   double* CE2 = g02 + c * n;
   double* ce02 = CE2 + c * n * p;
@@ -505,8 +511,6 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = fail(MGQP_ERR_CUDA, "retry kernels failed: %s", cudaGetErrorString(e));
   }
-  cudaFreeAsync(ws, st);
-  cudaFreeAsync(idx, st);
   return rc;
 }
 
