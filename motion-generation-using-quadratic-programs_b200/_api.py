@@ -184,10 +184,29 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
             raise ValueError("CI_val (float64) and CI_row (uint8) go together")
         if tuple(CI_val.shape[1:]) != (m,) or tuple(CI_row.shape[1:]) != (m,):
             raise LogicError(f"The compressed CI is incompatible (expecting [B, {m}])")
-        CI_val, CI_row = CI_val.contiguous(), CI_row.contiguous()
         if CI is None:
             CI = torch.empty((1, n, m), dtype=torch.float64, device=dev)  # never read
     B = max(t.shape[0] for t in (G, g0, CE, ce0, CI, ci0))
+    if CI_val is not None and (CI_val.shape[0] not in (1, B) or CI_row.shape[0] not in (1, B)):
+        raise ValueError("leading dimensions of CI_val / CI_row must be B or 1")
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+    # Temporaries (contiguous copies) are produced on torch's current stream and handed back to its caching
+    # allocator when this function returns; on a foreign stream nothing would order either against the
+    # asynchronous solver launch.  There the caller must pass contiguous tensors.
+    foreign = sptr != torch.cuda.current_stream(dev).cuda_stream
+
+    def _contig(t):
+        if t.numel() == 0 or t[0].is_contiguous():
+            return t
+        if foreign:
+            raise ValueError("non-contiguous input with a stream that is not torch's current stream: "
+                             "make the tensor contiguous on that stream first")
+        return t.contiguous()
+
+    if CI_val is not None:
+        CI_val, CI_row = _contig(CI_val), _contig(CI_row)
     _validate_shapes(n, p, m, tuple(G.shape[1:]), tuple(g0.shape[1:]), tuple(CE.shape[1:]), tuple(ce0.shape[1:]),
                      tuple(CI.shape[1:]), tuple(ci0.shape[1:]))
     ts = []
@@ -196,7 +215,7 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
             raise ValueError("all inputs must be float64")
         if t.shape[0] not in (1, B):
             raise ValueError("leading dimensions must be B or 1")
-        ts.append(t if t.numel() == 0 or t[0].is_contiguous() else t.contiguous())
+        ts.append(_contig(t))
     G, g0, CE, ce0, CI, ci0 = ts
     if out is None:
         x = torch.empty((B, n), dtype=torch.float64, device=dev)
@@ -227,9 +246,6 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
         d.CI_val, d.CI_row = CI_val.data_ptr(), CI_row.data_ptr()
         d.sCIv = 0 if CI_val.shape[0] == 1 and B > 1 else m
         d.sCIr = 0 if CI_row.shape[0] == 1 and B > 1 else m
-    if stream is None:
-        stream = torch.cuda.current_stream(dev)
-    sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
     _check(lib().solve_quadprog_batched(C.byref(d), dev.index if dev.index is not None else 0, C.c_void_p(sptr)))
     return out
 
@@ -238,10 +254,20 @@ def solve_quadprog_batched(G, g0, CE, ce0, CI, ci0, *, want_active_set: bool = F
 def _host_desc(G, g0, CE, ce0, CI, ci0, want_active_set, max_iter, flags, outs=None):
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (G, g0, CE, ce0, CI, ci0)]
     G, g0, CE, ce0, CI, ci0 = arrs
-    B, n = g0.shape
+    names = ("G", "g0", "CE", "ce0", "CI", "ci0")
+    for name, a, nd in zip(names, arrs, (3, 2, 3, 2, 3, 2)):
+        if a.ndim != nd:
+            raise ValueError(f"{name} must have {nd} dimensions ([B, ...]; a leading 1 broadcasts), got shape {a.shape}")
+    n = g0.shape[1]
     p = ce0.shape[1]
     m = ci0.shape[1]
     _validate_shapes(n, p, m, G.shape[1:], g0.shape[1:], CE.shape[1:], ce0.shape[1:], CI.shape[1:], ci0.shape[1:])
+    # The C side walks every field with batch * stride: a field shorter than the batch would be read
+    # past its end.  Leading dimension B, or 1 = one instance for the whole batch (stride 0).
+    B = max(a.shape[0] for a in arrs)
+    for name, a in zip(names, arrs):
+        if a.shape[0] not in (1, B):
+            raise ValueError(f"{name} has leading dimension {a.shape[0]}; expecting the batch size {B} or 1 (broadcast)")
     if outs is None:
         x = np.empty((B, n))
         f = np.empty(B)
@@ -252,13 +278,16 @@ def _host_desc(G, g0, CE, ce0, CI, ci0, want_active_set, max_iter, flags, outs=N
             A = np.empty((B, p + m), dtype=np.int32)
             iters = np.empty(B, dtype=np.int32)
         outs = QPResult(x, f, status, iq, A, iters)
+    else:
+        if outs.x.shape != (B, n) or outs.f.shape != (B,) or outs.status.shape != (B,):
+            raise ValueError(f"out buffers do not match the batch ([{B}, {n}], [{B}], [{B}])")
     d = mgqp_batch()
     d.n, d.p, d.m, d.batch = n, p, m, B
     nat = (n * n, n, n * p, p, n * m, m)
     dummy = outs.x
-    for name, a, na in zip(("G", "g0", "CE", "ce0", "CI", "ci0"), arrs, nat):
+    for name, a, na in zip(names, arrs, nat):
         setattr(d, name, a.ctypes.data if a.size else dummy.ctypes.data)
-        setattr(d, "s" + name, na)
+        setattr(d, "s" + name, 0 if (a.shape[0] == 1 and B > 1) else na)
     d.x, d.f, d.status = outs.x.ctypes.data, outs.f.ctypes.data, outs.status.ctypes.data
     d.iq = outs.iq.ctypes.data if outs.iq is not None else None
     d.A = outs.A.ctypes.data if outs.A is not None else None

@@ -205,9 +205,15 @@ int launch_lane(DeviceCtx* ctx, const LanePlan& lp, const LaneParams& P, cudaStr
       ctx->lane_attr_smem[N][FMA] = lp.smem;
     }
   }
+  if (const char* e = std::getenv("MGQP_LANE_CARVEOUT"))  // tuning knob: shared-memory carve-out in percent
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lp.warps * 32, lp.smem));
   if (per_sm < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "lane kernel does not fit an SM (smem %d B)", lp.smem);
+  if (const char* e = std::getenv("MGQP_LANE_CTAS_PER_SM")) {  // tuning knob: fewer resident CTAs per SM
+    const int c = std::atoi(e);
+    if (c >= 1 && c < per_sm) per_sm = c;
+  }
   long long ctas = (long long)ctx->sms * per_sm;
   const long long need = (P.tiles + lp.warps - 1) / lp.warps;
   if (ctas > need) ctas = need;

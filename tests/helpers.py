@@ -23,8 +23,17 @@ def assert_bit_identical(got, ref, what=""):
     for k in ("status", "iq", "A", "iters"):
         if k in got and got[k] is not None and k in ref:
             assert np.array_equal(got[k], ref[k]), f"{what}: {k} differs at {np.nonzero(np.atleast_1d(got[k] != ref[k]))[0][:5]}"
-    assert np.array_equal(got["x"], ref["x"], equal_nan=True), f"{what}: x not bit-identical"
-    assert np.array_equal(got["f"], ref["f"], equal_nan=True), f"{what}: f not bit-identical"
+    for k in ("x", "f"):
+        _assert_same_bits(got[k], ref[k], f"{what}: {k}")
+
+
+def _assert_same_bits(a, b, what):
+    """Equality of the fp64 BIT patterns (so -0.0 != +0.0), any NaN matching any NaN."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    same = (a.view(np.int64) == b.view(np.int64)) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), f"{what} not bit-identical at {np.argwhere(~same)[:5].tolist()}"
 
 
 def assert_parity(got, ref, what="", rtol=RTOL):
