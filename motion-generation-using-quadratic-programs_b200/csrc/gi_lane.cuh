@@ -7,29 +7,40 @@
 //
 // Why a second kernel family: with n = 7 a lane group of 8 (gi_small.cuh) spends most of its issue
 // slots on work that is uniform across the group (divisions, square roots, control) and on ordered
-// cross-lane sums; one lane per QP executes each of those once per QP.  The price is shared
-// memory: a lane owns a private, bank-skewed slot, so the constraint matrix cannot stay resident
-// in dense form.  Instead each inequality column is classified while it streams in from HBM (its
-// only read):
-//     * at most one nonzero  -> kept as (row, value): joint acceleration / velocity / position /
-//       torque bounds, i.e. every inequality the reference itself ever builds
-//       (src/mgqp.cpp:1080-1128, limitsMatrix = [-I; +I]);
-//     * anything else        -> marked DENSE and re-read from global memory (L2) when scanned.
-// The compressed form is used ONLY in the violated-constraint scan, and only while x is finite:
-// sum_j CI[j][i]*x[j] with exact-zero coefficients equals 0.0 + v*x[k] bit for bit.  Everything
-// else (compute_d, step lengths, the s[ip] refresh) works on the dense column np = CI[:,ip].
+// cross-lane sums; one lane per QP executes each of those once per QP.
+//
+// A tile (32 QPs) goes through five phases:
+//   A  cooperative, coalesced stage-in of G and g0: consecutive lanes copy consecutive doubles of the
+//      tile's block (cp.async, 8 bytes each) into the OWNER lane's private shared-memory slot;
+//   S  lane-owned set-up (Cholesky of G, J = L^-T, x0 = -G^-1 g0) in the reference's operation order;
+//   B  cooperative, coalesced classification of the inequality block: lane l takes column c of QP q
+//      ((q, c) enumerate the tile's 32*m columns), reads its n coefficients -- 32 lanes read 32
+//      consecutive doubles of a row of CI -- and writes ONE byte into the owner's slot:
+//        * a single nonzero coefficient equal to +1 or -1 -> the index of +x_k / -x_k in a small table
+//          (every inequality the reference itself ever builds: src/mgqp.cpp:1111-1112,
+//          limitsMatrix = [-I; +I]);
+//        * no nonzero coefficient                          -> the index of the table's 0.0 entry;
+//        * anything else (GEN)                              -> the column is re-read from global memory
+//          (L2) whenever it is scanned, with the reference's full n-term sum.
+//      ci0 is copied into the slot by cp.async on the way;
+//   I  the active-set iteration, lane-owned: J lives in REGISTERS, the rest of a lane's state in its slot;
+//   O  results (x through shared memory so that the global stores are coalesced).
+// With the +-1 columns reduced to one byte each the slot is 107 doubles at n = 7, m = 42 (it was 149
+// when every column kept a coefficient), which is what lets eight warps share an SM.
+//
+// The byte form is used ONLY in the violated-constraint scan, and only while x is finite:
+// sum_j CI[j][i]*x[j] with exact-zero coefficients and a +-1 equals +-x[k] bit for bit (up to the sign
+// of a zero, which no comparison can see).  Everything else (compute_d, step lengths, the s[ip]
+// refresh) works on the dense column np = CI[:,ip].
 //
 // Each lane runs the reference's scalar recurrences in the reference's own operation order, so
 // results are bit-identical to QuadProg++ by construction (no cross-lane arithmetic at all).
 //
-// The set-up (Cholesky of G, J = L^-T, x0 = -G^-1 g0) is fully unrolled over the compile-time N and
-// lives in registers: G and g0 go from global memory straight into registers; J never leaves them.  The 49 + 21 + 14 IEEE divisions of that phase are independent across rows, which is
-// where a lone warp per scheduler gets its instruction-level parallelism from.
-//
 // Slot layout (doubles; the lane stride is odd so the 16 lanes of a half warp hit 16 distinct
 // 8-byte bank pairs whenever they address the same element):
-//   R (upper Hessenberg, packed) | d[N] (doubles as the x mirror during scans) | r[N] | u[N+1] |
-//   civ[m] | ci0[m] | int8: A[N+1], A_old[N+1], cidx[m]          (J and u_old live in registers)
+//   area A: R (upper Hessenberg, packed) | d[N] | r[N] | zero | u[N+1]      (set-up: J scratch | g0/y/x)
+//   area B: ci0[m] | int8: A[N+1], A_old[N+1], gen, cidx[m]                 (set-up: L)
+// d | r | zero double as the scan's table [x | -x | 0.0] (d and r are dead while a scan runs).
 #pragma once
 #include "warp_prims.cuh"
 
@@ -42,25 +53,33 @@
 #define MGQP_LDG2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
 #define MGQP_LDG2_STREAM(p, a, b) MGQP_LDG2(p, a, b)
 #define MGQP_PREFETCH_L2(p) do { } while (0)
+#define MGQP_CP8(dst, src) (*(dst) = *(src))
+#define MGQP_CP_WAIT() do { } while (0)
+#define MGQP_OPAQUE_PTR(p) do { } while (0)
 #else
+// hide a pointer's derivation from the optimiser, so that `p + i` stays ONE 64-bit multiply-add on a 32-bit i
+// instead of being re-associated into 64-bit index arithmetic
+#define MGQP_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
 #define MGQP_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define MGQP_LDG(p) __ldg(p)
 #define MGQP_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
-// streaming 16-byte load that is cached in L2 only: each lane touches its own 128-byte lines, and the
-// few KB of L1 left beside 224 KB of shared memory cannot hold them until their other sectors are read
 #define MGQP_LDG2_STREAM(p, a, b) asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p))
+// 8-byte asynchronous copy global -> shared: no register, no scoreboard; completion by MGQP_CP_WAIT
+#define MGQP_CP8(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define MGQP_CP_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #endif
 
-#ifndef MGQP_LANE_PQ
-#define MGQP_LANE_PQ 1
+#ifndef MGQP_LANE_K
+#define MGQP_LANE_K 2
 #endif
 
 namespace mgqp {
 
 struct LaneView {
   int n, p, m;
-  int oR, od, orr, ou, ociv, oci0, oByte;               // doubles
-  int bA, bAold, bcidx;                                // bytes, relative to (signed char*)(slot + oByte)
+  int oR, od, orr, ozero, ou, oci0, oByte;            // doubles
+  int oJs, ov, oLs;                                    // set-up scratch (doubles)
+  int bA, bAold, bgen, bcidx;                          // bytes, relative to (signed char*)(slot + oByte)
   int stride;                                          // doubles per lane, odd
 };
 
@@ -76,26 +95,33 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
   v.oR = o;     o += lane_rh_size(n);
   v.od = o;     o += n;
   v.orr = o;    o += n;
+  v.ozero = o;  o += 1;
   v.ou = o;     o += n + 1;
-  v.ociv = o;   o += m;
-  v.oci0 = o;   o += m;
-  // the civ|ci0 area doubles as set-up scratch (L | y | x | g0), the R|d|r|u area as scratch for J
-  if (2 * m < n * n + 3 * n) o += n * n + 3 * n - 2 * m;
-  v.oByte = o;
+  // set-up scratch in area A: J (n*n) | g0 -> y -> x (n)
+  v.oJs = 0;
+  v.ov = n * n;
+  if (o < n * n + n) o = n * n + n;
+  v.oci0 = o;
+  v.oLs = o;    // set-up scratch in area B: the Cholesky factor (n*n)
+  const int bytes = 2 * (n + 1) + 1 + m;
+  int b = m + (bytes + 7) / 8;
+  if (b < n * n) b = n * n;
+  v.oByte = o + m;
+  o += b;
   v.bA = 0;
   v.bAold = n + 1;
-  v.bcidx = 2 * (n + 1);
-  const int bytes = 2 * (n + 1) + m;
-  o += (bytes + 7) / 8;
+  v.bgen = 2 * (n + 1);
+  v.bcidx = 2 * (n + 1) + 1;
   if ((o & 1) == 0) o++;  // odd stride: the 16 lanes of a half warp land on 16 distinct 8-byte bank pairs
   v.stride = o;
   return v;
 }
 
-// per-column byte: ONE (a nonzero has been seen) | DENSE (more than one) | bits 3-5 row of the single
-// nonzero, i.e. its byte offset into a vector of doubles | EXCL (iaexcl == false) | ACT (iai == -1).
-// A column may be chosen iff byte < LN_EXCL.
-enum { LN_ONE = 0x01, LN_DENSE = 0x02, LN_ROW = 0x38, LN_ROW_SHIFT = 3, LN_EXCL = 0x40, LN_ACT = 0x80 };
+// per-column byte: bits 3-7 = byte offset (index * 8) into the table [x_0..x_{N-1} | -x_0..-x_{N-1} | 0.0]
+// of the term the column contributes to s_i (GEN columns: the row of the single nonzero, where known);
+// GEN = the column needs the reference's full sum; EXCL (iaexcl == false) | ACT (iai == -1).
+// A column may be chosen iff (byte & (EXCL | ACT)) == 0.
+enum { LN_GEN = 0x01, LN_EXCL = 0x02, LN_ACT = 0x04, LN_IDX = 0xf8, LN_IDX_SHIFT = 3 };
 
 MGQP_DEV double ln_distance(double a, double b) {
   // One division and one square root whichever argument is the larger: the two branches of the reference
@@ -136,101 +162,6 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
   return g;
 }
 
-// Stream this lane's CI (N x m, row-major) and ci0 from global memory -- their only read -- and sort the
-// inequality columns into (row, value) form: cidx[i] = flag byte, civ[i] = the single nonzero coefficient
-// (+-0.0 for an empty column), sci0[i] = ci0[i].  Returns true iff some column has more than one nonzero.
-// PQ = 1: with two or three pairs per chunk (or a three-deep ring) ptxas spills the load buffers, and
-// as a separate non-inlined routine the call ABI costs more than it buys (measured, profiles/r01_notes.md).
-template <int N>
-MGQP_DEV bool ln_classify(const double* __restrict__ CI, const double* __restrict__ ci0, int m,
-                                   double* __restrict__ civ, double* __restrict__ sci0, unsigned char* __restrict__ cidx) {
-  bool has_dense = false;
-  const bool vec = ((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(CI) & 15ull) == 0ull) &&
-                   ((reinterpret_cast<unsigned long long>(ci0) & 15ull) == 0ull);
-  if (vec) {
-    // PQ column pairs (one 16-byte load per row of CI, plus one of ci0, per pair) per chunk, the next
-    // chunk's PQ*(N+1) loads in flight while the current one is classified.  Per element: one compare,
-    // one add into the column's running sum and one conditional integer add into its (count, row)
-    // word -- with at most one nonzero in a column the sum IS that coefficient bit for bit
-    // (v + (+-0.0) == v), and count*64 + 8*row is the flag byte.
-    constexpr int PQ = MGQP_LANE_PQ;
-    const int mh = m >> 1;
-    double bufA[PQ][N + 1][2], bufB[PQ][N + 1][2];
-    auto load_chunk = [&](double (&b)[PQ][N + 1][2], int c) {
-#pragma unroll
-      for (int q = 0; q < PQ; q++)
-        if (c + q < mh) {
-#pragma unroll
-          for (int j = 0; j < N; j++) MGQP_LDG2_STREAM(CI + j * m + 2 * (c + q), b[q][j][0], b[q][j][1]);
-          MGQP_LDG2_STREAM(ci0 + 2 * (c + q), b[q][N][0], b[q][N][1]);
-        }
-    };
-    auto sort_chunk = [&](const double (&b)[PQ][N + 1][2], int c) {
-#pragma unroll
-      for (int q = 0; q < PQ; q++)
-        if (c + q < mh) {
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            double val = b[q][0][h];
-            unsigned acc = (b[q][0][h] != 0.0) ? 64u : 0u;  // NaN counts as nonzero
-#pragma unroll
-            for (int j = 1; j < N; j++) {
-              val = d_add(val, b[q][j][h]);
-              if (b[q][j][h] != 0.0) acc += 64u + 8u * j;
-            }
-            const int i = 2 * (c + q) + h;
-            unsigned byte = (acc & LN_ROW) | LN_ONE;
-            if (acc < 64u) byte = 0;
-            if (acc >= 128u) {
-              byte = LN_ONE | LN_DENSE;
-              has_dense = true;
-            }
-            cidx[i] = (unsigned char)byte;
-            civ[i] = val;
-            sci0[i] = b[q][N][h];
-          }
-        }
-    };
-    // (All of these loads share one hardware scoreboard -- ptxas' choice -- so the first use of a buffer
-    // also waits for the loads issued after it: each trip of this loop exposes one full round trip to L2
-    // whatever the order of its four stages.  Ordering fences and a three-deep ring were measured: no gain.)
-    load_chunk(bufA, 0);
-#pragma unroll 1
-    for (int c = 0; c < mh; c += 2 * PQ) {
-      load_chunk(bufB, c + PQ);
-      sort_chunk(bufA, c);
-      load_chunk(bufA, c + 2 * PQ);
-      sort_chunk(bufB, c + PQ);
-    }
-  } else {
-    // odd m or unaligned fields: element-wise row sweep
-#pragma unroll 1
-    for (int i = 0; i < m; i++) {
-      cidx[i] = 0;
-      civ[i] = 0.0;
-      sci0[i] = MGQP_LDG(ci0 + i);
-    }
-#pragma unroll 1
-    for (int j = 0; j < N; j++) {
-      const double* row = CI + j * m;
-#pragma unroll 4
-      for (int i = 0; i < m; i++) {
-        const double a = MGQP_LDG(row + i);
-        if (a != 0.0) {  // NaN counts as nonzero
-          if (!(cidx[i] & LN_ONE)) {
-            cidx[i] = (unsigned char)((j << LN_ROW_SHIFT) | LN_ONE);
-            civ[i] = a;
-          } else {
-            cidx[i] |= LN_DENSE;
-            has_dense = true;
-          }
-        }
-      }
-    }
-  }
-  return has_dense;
-}
-
 struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
   // lane kernel only: column-compressed CI (mgqp_batch::CI_val / CI_row); CI is unused when CIv is set
@@ -238,48 +169,296 @@ struct LaneIO {  // global memory, this lane's QP
   const unsigned char* CIr = nullptr;
 };
 
-// Column-compressed constraints as they come from the caller (or from the host pipeline's packer): the
-// (row, value) form the classification would have produced, taken as is.  A row index >= N cannot come
-// from a well-formed batch; it is clamped so that a corrupt one stays inside the lane's slot.
+// Global memory of one tile: the fields of the tile's FIRST QP and the element strides between QPs.
+struct LaneTileIO {
+  const double* in[6];        // G, g0, CE, ce0, CI, ci0
+  long long stride[6];
+  const double* CIv = nullptr;  // column-compressed CI (mgqp_batch::CI_val / CI_row) or null
+  const unsigned char* CIr = nullptr;
+  long long sCIv = 0, sCIr = 0;
+  int cnt = 32;               // QPs in the tile (lanes >= cnt replicate QP 0 and store nothing)
+  const double* next_G = nullptr;   // the G / g0 blocks of the tile this warp will take next (L2 prefetch), or null
+  const double* next_g0 = nullptr;
+};
+
+// Flat enumeration of (QP q, element k) pairs of a tile with L elements per QP: lane l takes pairs
+// l, l + 32, ...; running offsets into the global block (element stride sg between QPs) and into the
+// slots (stride ss), no division or 64-bit multiply inside the loops.
+struct LaneWalk {
+  int q, k, L, dq, dk;
+  long long soff, sstep, swrap;
+  int doff, dstep, dwrap;
+  MGQP_MEMBER void init(int lane, int L_, long long sg, int ss) {
+    L = L_;
+    dq = 32 / L; dk = 32 - dq * L;
+    q = lane / L; k = lane - q * L;
+    soff = q * sg + k; sstep = dq * sg + dk; swrap = sg - L;
+    doff = q * ss + k; dstep = dq * ss + dk; dwrap = ss - L;
+  }
+  MGQP_MEMBER void next() {
+    q += dq; k += dk; soff += sstep; doff += dstep;
+    if (k >= L) { k -= L; q++; soff += swrap; doff += dwrap; }
+  }
+};
+
+// A tile is NATURAL when it is full and each of its G, g0, CI and ci0 blocks is one contiguous array (the
+// fields' natural strides, no compressed CI): the common case, served by loops whose global offsets are
+// 32-bit and mostly compile-time.
 template <int N>
-MGQP_DEV void ln_take_compressed(const double* __restrict__ CIv, const unsigned char* __restrict__ CIr,
-                                 const double* __restrict__ ci0, int m, double* __restrict__ civ,
-                                 double* __restrict__ sci0, unsigned char* __restrict__ cidx) {
-  const bool vec = ((m & 1) == 0) && ((reinterpret_cast<unsigned long long>(CIv) & 15ull) == 0ull) &&
-                   ((reinterpret_cast<unsigned long long>(ci0) & 15ull) == 0ull);
-  if (vec) {
-#pragma unroll 7
-    for (int i = 0; i < m; i += 2) {
-      double a0, a1, b0, b1;
-      MGQP_LDG2(CIv + i, a0, a1);
-      MGQP_LDG2(ci0 + i, b0, b1);
-      civ[i] = a0; civ[i + 1] = a1;
-      sci0[i] = b0; sci0[i + 1] = b1;
-    }
-  } else {
-#pragma unroll 4
-    for (int i = 0; i < m; i++) {
-      civ[i] = MGQP_LDG(CIv + i);
-      sci0[i] = MGQP_LDG(ci0 + i);
-    }
-  }
-#pragma unroll 4
-  for (int i = 0; i < m; i++) {
-    unsigned r = MGQP_LDG(CIr + i);
-    r = r < (unsigned)N ? r : (unsigned)(N - 1);
-    cidx[i] = (unsigned char)((r << LN_ROW_SHIFT) | LN_ONE);
-  }
+MGQP_DEV bool ln_tile_is_natural(const LaneView& v, const LaneTileIO& t) {
+  return t.cnt == 32 && !t.CIv && t.stride[0] == N * N && t.stride[1] == N && t.stride[4] == (long long)N * v.m &&
+         t.stride[5] == v.m;
 }
 
+// pull the NEXT tile's G / g0 blocks towards L2 (natural strides assumed: a wrong guess only wastes a prefetch)
+MGQP_DEV void ln_prefetch_next(const LaneTileIO& t, int n) {
+  if (!t.next_G) return;
+  const int lane = wp_lane();
+  const char* p = reinterpret_cast<const char*>(t.next_G);
+#pragma unroll 1
+  for (int o = lane * 128; o < 32 * n * n * 8; o += 32 * 128) MGQP_PREFETCH_L2(p + o);
+  const char* p0 = reinterpret_cast<const char*>(t.next_g0);
+#pragma unroll 1
+  for (int o = lane * 128; o < 32 * n * 8; o += 32 * 128) MGQP_PREFETCH_L2(p0 + o);
+}
+
+// pull the tile's CI / ci0 blocks towards L2 while phases A and S run (phase B reads them)
+MGQP_DEV void ln_prefetch_CI(const LaneView& v, const LaneTileIO& t, int n) {
+  const int lane = wp_lane();
+  const char* p = reinterpret_cast<const char*>(t.in[4]);
+  const int bytes = 32 * n * v.m * 8;
+#pragma unroll 4
+  for (int o = lane * 128; o < bytes; o += 32 * 128) MGQP_PREFETCH_L2(p + o);
+  const char* p0 = reinterpret_cast<const char*>(t.in[5]);
+#pragma unroll 1
+  for (int o = lane * 128; o < 32 * v.m * 8; o += 32 * 128) MGQP_PREFETCH_L2(p0 + o);
+}
+
+// ---- phase A: G and g0 of the tile's QPs into the owners' slots (L scratch, g0/y/x scratch).
+template <int N>
+MGQP_DEV void ln_stage_G(const LaneView& v, double* __restrict__ ws, const LaneTileIO& t, bool natural) {
+  const int lane = wp_lane();
+  if (natural) {
+    {
+      constexpr int L = N * N, dq = 32 / L, dk = 32 - dq * L;
+      const double* __restrict__ src = t.in[0] + lane;
+      int k = lane % L;
+      int doff = (lane / L) * v.stride + k;
+      const int dstep = dq * v.stride + dk, dwrap = v.stride - L;
+      double* dst = ws + v.oLs;
+#pragma unroll 7
+      for (int r = 0; r < L; r++) {  // 32 * N*N elements = N*N rounds of 32 lanes
+        MGQP_CP8(dst + doff, src + 32 * r);
+        k += dk; doff += dstep;
+        if (k >= L) { k -= L; doff += dwrap; }
+      }
+    }
+    {
+      constexpr int L = N, dq = 32 / L, dk = 32 - dq * L;
+      const double* __restrict__ src = t.in[1] + lane;
+      int k = lane % L;
+      int doff = (lane / L) * v.stride + k;
+      const int dstep = dq * v.stride + dk, dwrap = v.stride - L;
+      double* dst = ws + v.ov;
+#pragma unroll
+      for (int r = 0; r < L; r++) {
+        MGQP_CP8(dst + doff, src + 32 * r);
+        k += dk; doff += dstep;
+        if (k >= L) { k -= L; doff += dwrap; }
+      }
+    }
+  } else {
+    {
+      const double* __restrict__ G = t.in[0];
+      LaneWalk w;
+      w.init(lane, N * N, t.stride[0], v.stride);
+      double* dst = ws + v.oLs;
+#pragma unroll 1
+      for (int r = 0; r < N * N; r++) {
+        MGQP_CP8(dst + w.doff, G + (w.q < t.cnt ? w.soff : (long long)w.k));
+        w.next();
+      }
+    }
+    {
+      const double* __restrict__ g0 = t.in[1];
+      LaneWalk w;
+      w.init(lane, N, t.stride[1], v.stride);
+      double* dst = ws + v.ov;
+#pragma unroll 1
+      for (int r = 0; r < N; r++) {
+        MGQP_CP8(dst + w.doff, g0 + (w.q < t.cnt ? w.soff : (long long)w.k));
+        w.next();
+      }
+    }
+  }
+  MGQP_CP_WAIT();
+}
+
+// One inequality column -> its byte.  `acc` counts 64 per nonzero entry and adds 8 * row; `val` is the ordered
+// sum of the column, which IS the single nonzero bit for bit when there is exactly one (v + (+-0.0) == v).
+// (-0.0 counts as a zero: every use of a coefficient is a product added to a sum that starts at +0.0, where
+// the sign of a zero coefficient cannot show.)
+template <int N>
+MGQP_DEV unsigned ln_column_byte(unsigned acc, double val) {
+  unsigned byte = LN_GEN | (acc & 0x38u);                            // one nonzero, not a unit: exact path
+  if (val == 1.0) byte = acc & 0x38u;                                // +x_k
+  if (val == -1.0) byte = (acc & 0x38u) + (unsigned)(8 * N);         // -x_k
+  if (acc >= 128u) byte = LN_GEN;                                    // two or more nonzeros
+  if (acc < 64u) byte = (unsigned)(2 * N) << LN_IDX_SHIFT;           // empty column: contributes +0.0
+  return byte;
+}
+
+// ---- phase B: classify the tile's 32*m inequality columns, lane l <-> columns l, l+32, ... of the flat
+// (QP, column) enumeration; copy ci0 into the slots.  Every load is one row segment of CI: coalesced.
+// Lanes beyond the tile's last QP get empty columns with ci0 = 1 (always satisfied).
+template <int N>
+MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const LaneTileIO& t, bool natural) {
+  const int m = v.m;
+  if (m <= 0) return;
+  const int lane = wp_lane();
+  const double* __restrict__ ci0 = t.in[5];
+  unsigned char* bytes = reinterpret_cast<unsigned char*>(ws + v.oByte) + v.bcidx;
+  unsigned char* gen = reinterpret_cast<unsigned char*>(ws + v.oByte) + v.bgen;
+  double* dci0 = ws + v.oci0;
+  if (natural) {
+    // the tile's CI block is one array: column (q, c), row j sits at q*N*m + j*m + c = e + j*m with
+    // e = t + q*(N-1)*m, t = q*m + c the flat column number (lane, lane + 32, ...)
+    const double* __restrict__ CI = t.in[4];
+    const double* rowp[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      rowp[j] = CI + j * m;
+      MGQP_OPAQUE_PTR(rowp[j]);
+    }
+    const int dq = 32 / m, dc = 32 - dq * m;
+    int q = lane / m, c = lane - q * m;
+    unsigned tt = lane, e = lane + q * (N - 1) * m;
+    int doff = q * v.stride + c;
+    const int dstep = dq * v.stride + dc, dwrap = v.stride - m;
+    const unsigned de = 32 + dq * (N - 1) * m, ewrap = (N - 1) * m;
+    constexpr int K = MGQP_LANE_K;               // columns per trip: K*N loads in flight per lane
+#pragma unroll 1
+    for (int r0 = 0; r0 < m; r0 += K) {
+      double b[K][N];
+      int c_[K], doff_[K];
+      unsigned t_[K];
+#pragma unroll
+      for (int u = 0; u < K; u++) {
+        if (r0 + u < m) {  // warp-uniform
+#pragma unroll
+          for (int j = 0; j < N; j++) b[u][j] = MGQP_LDG(rowp[j] + e);
+          c_[u] = c; doff_[u] = doff; t_[u] = tt;
+          tt += 32; c += dc; e += de; doff += dstep;
+          if (c >= m) { c -= m; e += ewrap; doff += dwrap; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < K; u++) {
+        if (r0 + u < m) {
+          double val = b[u][0];
+          unsigned acc = (b[u][0] != 0.0) ? 64u : 0u;  // NaN counts as nonzero
+#pragma unroll
+          for (int j = 1; j < N; j++) {
+            val = d_add(val, b[u][j]);
+            if (b[u][j] != 0.0) acc += 64u + 8u * j;
+          }
+          const unsigned byte = ln_column_byte<N>(acc, val);
+          MGQP_CP8(dci0 + doff_[u], ci0 + t_[u]);
+          bytes[8 * doff_[u] - 7 * c_[u]] = (unsigned char)byte;
+          if (byte & LN_GEN) gen[8 * (doff_[u] - c_[u])] = 1;
+        }
+      }
+    }
+    MGQP_CP_WAIT();
+    return;
+  }
+  LaneWalk w;                                  // source offsets: the ci0 block ([q][c], stride sci0)
+  w.init(lane, m, t.stride[5], v.stride);
+  auto finish = [&](int q, int k, int doff, long long soff, unsigned byte) {
+    // slot byte address: q * stride * 8 + k  ==  8 * (doff - k) + k
+    const int boff = 8 * (doff - k) + k;
+    if (q < t.cnt) {
+      MGQP_CP8(dci0 + doff, ci0 + soff);
+    } else {
+      dci0[doff] = 1.0;
+      byte = (unsigned)(2 * N) << LN_IDX_SHIFT;
+    }
+    bytes[boff] = (unsigned char)byte;
+    if (byte & LN_GEN) gen[8 * (doff - k)] = 1;
+  };
+  if (t.CIv) {
+    // the caller's (or the host packer's) column-compressed form: (value, row) per column
+    long long so = w.q * t.sCIv + w.k, ro = w.q * t.sCIr + w.k;
+    const long long sstep = w.dq * t.sCIv + w.dk, swrap = t.sCIv - m, rstep = w.dq * t.sCIr + w.dk, rwrap = t.sCIr - m;
+#pragma unroll 2
+    for (int r = 0; r < m; r++) {
+      unsigned byte = 0;
+      if (w.q < t.cnt) {
+        const double a = MGQP_LDG(t.CIv + so);
+        unsigned row = MGQP_LDG(t.CIr + ro);
+        row = row < (unsigned)N ? row : (unsigned)(N - 1);  // a corrupt batch stays inside the table
+        byte = ln_column_byte<N>((a != 0.0 ? 64u : 0u) + 8u * row, a);
+      }
+      finish(w.q, w.k, w.doff, w.soff, byte);
+      const int k0 = w.k;
+      w.next();
+      so += sstep; ro += rstep;
+      if (w.k < k0 + w.dk) { so += swrap; ro += rwrap; }  // the walk wrapped into the next QP
+    }
+  } else {
+    // strided fields or a partial tile: one column per trip
+    const double* __restrict__ CI = t.in[4];
+    const long long sCI = t.stride[4];
+    long long co = w.q * sCI + w.k;              // offset of CI[q][0][k]
+    const long long cstep = w.dq * sCI + w.dk, cwrap = sCI - m;
+#pragma unroll 1
+    for (int r = 0; r < m; r++) {
+      unsigned byte = 0;
+      if (w.q < t.cnt) {
+        const double* src = CI + co;
+        double val = MGQP_LDG(src);
+        unsigned acc = (val != 0.0) ? 64u : 0u;
+#pragma unroll
+        for (int j = 1; j < N; j++) {
+          const double bj = MGQP_LDG(src + j * m);
+          val = d_add(val, bj);
+          if (bj != 0.0) acc += 64u + 8u * j;
+        }
+        byte = ln_column_byte<N>(acc, val);
+      }
+      finish(w.q, w.k, w.doff, w.soff, byte);
+      const int k0 = w.k;
+      w.next();
+      co += cstep;
+      if (w.k < k0 + w.dk) co += cwrap;
+    }
+  }
+  MGQP_CP_WAIT();
+}
+
+// One tile: lane `wp_lane()` owns QP `lane` of the tile (slot S = ws + lane * stride).
 template <int N, bool FMA>
-MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int max_iter, double* x_out,
-                            double& f_out, int& status_out, int& iq_out, int& iters_out) {
+MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const LaneTileIO& tio, int max_iter,
+                           double* x_out, double& f_out, int& status_out, int& iq_out, int& iters_out) {
   const int p = v.p, m = v.m;
+  const int lane = wp_lane();
+  const int myq = lane < tio.cnt ? lane : 0;
+  double* S = ws + lane * v.stride;
+  LaneIO io;
+  io.G = tio.in[0] + myq * tio.stride[0];
+  io.g0 = tio.in[1] + myq * tio.stride[1];
+  io.CE = tio.in[2] + myq * tio.stride[2];
+  io.ce0 = tio.in[3] + myq * tio.stride[3];
+  io.CI = tio.in[4] + myq * tio.stride[4];
+  io.ci0 = tio.in[5] + myq * tio.stride[5];
+  if (tio.CIv) {
+    io.CIv = tio.CIv + myq * tio.sCIv;
+    io.CIr = tio.CIr + myq * tio.sCIr;
+  }
   double* R = S + v.oR;
-  double* sd = S + v.od;  // d; reused as the smem mirror of x while scanning
+  double* sd = S + v.od;  // d; with r and the zero entry behind it: the scan's table [x | -x | 0.0]
   double* sr = S + v.orr;
   double* su = S + v.ou;
-  double* civ = S + v.ociv;
   double* sci0 = S + v.oci0;
   signed char* Bt = reinterpret_cast<signed char*>(S + v.oByte);
   signed char* A = Bt + v.bA;
@@ -289,38 +468,27 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
 
   int status = 0, iq = 0, steps = 0;
   double f = 0.0;
-  bool has_dense = false;  // some inequality column has more than one nonzero
   double x[N];
 #pragma unroll
   for (int i = 0; i < N; i++) x[i] = 0.0;
 
+  // ---------------------------------------------------------------- phase A: stage G, g0
+  const bool natural = ln_tile_is_natural<N>(v, tio);
+  if (natural && m > 0) ln_prefetch_CI(v, tio, N);
+  wp_sync();  // the previous tile's results have left the slots
+  ln_stage_G<N>(v, ws, tio, natural);
+  wp_sync();
+
   // ---------------------------------------------------------------- set-up
-  // Cholesky of G, J = L^-T and x0 = -G^-1 g0 run out of shared-memory scratch that the constraint
-  // data will occupy later (L | y | x | g0 in the civ/ci0 area, J in the R|d|r|u area), with the
-  // outer loops rolled and the independent rows unrolled: a fully unrolled register version was
-  // 4 000 instructions of straight-line code and made the kernel instruction-fetch bound.
-  // Pull this lane's constraint data towards L2 now; it is consumed right after the set-up (a
-  // whole-tile-ahead prefetch was evicted before use and doubled the DRAM traffic, this one is not).
-  {
-    const char* pc = reinterpret_cast<const char*>(io.CIv ? io.CIv : io.CI);
-    const int bytes = (io.CIv ? 1 : N) * m * 8;
-#pragma unroll 4
-    for (int o = 0; o < bytes; o += 128) MGQP_PREFETCH_L2(pc + o);
-    const char* p0 = reinterpret_cast<const char*>(io.ci0);
-#pragma unroll 1
-    for (int o = 0; o < m * 8; o += 128) MGQP_PREFETCH_L2(p0 + o);
-  }
-  double* Ls = S + v.ociv;
-  double* ys = Ls + N * N;
-  double* xs = ys + N;
-  double* g0s = xs + N;
-  double* Js = S + v.oR;
-  // (element-wise on purpose: 16-byte loads at each lane's own parity halve the requests but measured
-  // 4 % slower -- these loads hit L1 for the rest of each sector and are issued long before their use)
+  // Cholesky of G, J = L^-T and x0 = -G^-1 g0 run out of the slot (L in area B, J and g0 -> y -> x in
+  // area A), with the outer loops rolled and the independent rows unrolled: a fully unrolled register
+  // version was 4 000 instructions of straight-line code and made the kernel instruction-fetch bound.
+  double* Ls = S + v.oLs;
+  double* vs = S + v.ov;
+  double* Js = S + v.oJs;
+  double g0r[N];
 #pragma unroll
-  for (int i = 0; i < N * N; i++) Ls[i] = MGQP_LDG(io.G + i);
-#pragma unroll
-  for (int i = 0; i < N; i++) g0s[i] = MGQP_LDG(io.g0 + i);
+  for (int i = 0; i < N; i++) g0r[i] = vs[i];
   double c1 = 0.0;
 #pragma unroll
   for (int i = 0; i < N; i++) c1 = d_add(c1, Ls[i * N + i]);
@@ -363,12 +531,12 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     }
   }
 
+  double c2 = 0.0;
   if (fail) {
     status = 2;
     f = bad_pivot;
   } else {
     // J = L^-T: all N rows (row i = forward_elimination(L, e_i)) advance together, column by column
-    double c2 = 0.0;
 #pragma unroll 1
     for (int r = 0; r < N; r++) {
       double acc[N];
@@ -391,50 +559,54 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     }
 #pragma unroll
     for (int i = 0; i < N; i++) c2 = d_add(c2, Js[i * N + i]);
-    // x = -G^-1 g0 (cholesky_solve: forward then backward elimination), f = 0.5 g0.x
-    ys[0] = d_div(g0s[0], Ls[0]);
+    // x = -G^-1 g0 (cholesky_solve: forward then backward elimination, in place: g0 -> y -> x), f = 0.5 g0.x
+    vs[0] = d_div(vs[0], Ls[0]);
 #pragma unroll 1
     for (int i = 1; i < N; i++) {
-      double a = g0s[i];
+      double a = vs[i];
 #pragma unroll 2
-      for (int j = 0; j < i; j++) a = msub<FMA>(a, Ls[i * N + j], ys[j]);
-      ys[i] = d_div(a, Ls[i * N + i]);
+      for (int j = 0; j < i; j++) a = msub<FMA>(a, Ls[i * N + j], vs[j]);
+      vs[i] = d_div(a, Ls[i * N + i]);
     }
-    xs[N - 1] = d_div(ys[N - 1], Ls[(N - 1) * N + (N - 1)]);
+    vs[N - 1] = d_div(vs[N - 1], Ls[(N - 1) * N + (N - 1)]);
 #pragma unroll 1
     for (int i = N - 2; i >= 0; i--) {
-      double a = ys[i];
+      double a = vs[i];
 #pragma unroll 2
-      for (int j = i + 1; j < N; j++) a = msub<FMA>(a, Ls[i * N + j], xs[j]);
-      xs[i] = d_div(a, Ls[i * N + i]);
+      for (int j = i + 1; j < N; j++) a = msub<FMA>(a, Ls[i * N + j], vs[j]);
+      vs[i] = d_div(a, Ls[i * N + i]);
     }
     double fs = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      x[i] = -xs[i];
-      fs = mad<FMA>(g0s[i], x[i], fs);
+      x[i] = -vs[i];
+      fs = mad<FMA>(g0r[i], x[i], fs);
     }
     f = d_mul(0.5, fs);
-    // ---------------------------------------------------------------- inequality columns: classify
-    // (after the set-up, whose L | y | x | g0 scratch it overwrites; J waits in its own scratch so that
-    // the registers are free for the load pipeline)
-    if (m > 0) {
-      if (io.CIv) ln_take_compressed<N>(io.CIv, io.CIr, io.ci0, m, civ, sci0, cidx);
-      else has_dense = ln_classify<N>(io.CI, io.ci0, m, civ, sci0, cidx);
-    }
+  }
 
-    // J moves into REGISTERS for the rest of the solve: every access below has compile-time indices
-    // (the Givens sweeps are unrolled over the column index and predicated on the lane's own iq),
-    // which keeps J out of shared memory (6 resident warps per SM instead of 4) and removes ~100
-    // shared-memory loads from every iteration.
+  // ---------------------------------------------------------------- phase B: inequality columns
+  // (after the set-up, whose L scratch it overwrites)
+  Bt[v.bgen] = 0;
+  wp_sync();
+  ln_stage_CI<N>(v, ws, tio, natural);
+  if (natural) ln_prefetch_next(tio, N);
+  wp_sync();
+  const bool has_gen = Bt[v.bgen] != 0;  // some inequality column needs the reference's full sum
+
+  if (!fail) {
+    // J moves into REGISTERS for the rest of the solve (it waited in its scratch so that phase B had the
+    // registers for its loads): every access below has compile-time indices (the Givens sweeps are unrolled
+    // over the column index and predicated on the lane's own iq), which keeps J out of shared memory and
+    // removes ~100 shared-memory loads from every iteration.
     double Jr[N][N];
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll
       for (int j = 0; j < N; j++) Jr[i][j] = Js[i * N + j];
-
 #pragma unroll 1
     for (int i = 0; i < lane_rh_size(N); i++) R[i] = 0.0;
+    S[v.ozero] = 0.0;
 
     double R_norm = 1.0;
     const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
@@ -447,8 +619,6 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
     for (int i = 0; i < N; i++) { z[i] = 0.0; np[i] = 0.0; dd[i] = 0.0; }
     // The step-1 snapshot (x_old, u_old) is written every outer iteration but read back only on the
     // rare degenerate branch: it lives in thread-local memory on purpose (volatile keeps it there).
-    // Stores do not stall, and the 30 registers it would take otherwise made the compiler spill
-    // loop scalars whose reloads -- L1 is tiny next to 224 KB of shared memory -- cost an L2 round trip.
     volatile double xold[N], uold[N + 1];
 #pragma unroll
     for (int i = 0; i < N; i++) xold[i] = 0.0;
@@ -478,39 +648,60 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
         bool finite = true;
 #pragma unroll
         for (int j = 0; j < N; j++) {
-          sd[j] = x[j];  // x mirror (d is dead between add_constraint and the next direction)
+          sd[j] = x[j];   // the table [x | -x | 0.0] (d and r are dead between add_constraint and the next direction)
+          sr[j] = -x[j];
           finite = finite && (d_abs(x[j]) < INF);
         }
         double psi = 0.0;
         const double ss_in = ss;
-        if (!has_dense && finite) {
-          // every column is (row, value) or empty: s_i = v*x[row] + ci0_i equals the reference's N-term
-          // sum wherever a comparison can see it (the two can differ in the sign of a zero only)
+        if (!has_gen && finite) {
+          // every column is +-e_k or empty: s_i = +-x[k] + ci0_i equals the reference's N-term sum wherever a
+          // comparison can see it (the two can differ in the sign of a zero only)
+          const char* tab = reinterpret_cast<const char*>(sd);
 #pragma unroll 6
           for (int i = 0; i < m; i++) {
             const unsigned c = cidx[i];
-            const double sum = d_add(d_mul(civ[i], sd[(c & LN_ROW) >> LN_ROW_SHIFT]), sci0[i]);
-            d_acc_neg(psi, sum);  // psi += min(0, sum); a NaN sum adds nothing, as in the reference
-            if (sum < ss && c < LN_EXCL) {
+            const double sum = d_add(*reinterpret_cast<const double*>(tab + (c & LN_IDX)), sci0[i]);
+            if (sum < ss && !(c & (LN_EXCL | LN_ACT))) {
               ss = sum;
               ip = i;
             }
+          }
+          // psi = sum_i min(0, s_i) is only ever compared with thr (step 1: |psi| <= thr -> return f).  It is a
+          // sum of negative terms, so psi <= each of them (rounding is monotonic), in particular psi <= ss:
+          // whenever ss < -thr the test fails without psi being known.  And with ss >= 0 the outcome does not
+          // depend on it either: the reference returns the same f from step 1 or, a few lines later, from
+          // step 2.  Only a scan whose most violated eligible constraint lies within thr of feasibility
+          // needs the sum itself, in the reference's order.
+          if (l1 && ss < 0.0 && !(ss < -thr)) {
+#pragma unroll 1
+            for (int i = 0; i < m; i++) {
+              const unsigned c = cidx[i];
+              const double sum = d_add(*reinterpret_cast<const double*>(tab + (c & LN_IDX)), sci0[i]);
+              d_acc_neg(psi, sum);  // psi += min(0, sum); a NaN sum adds nothing, as in the reference
+            }
+          } else {
+            psi = -INF;  // stands for "fails the test" (with ss >= 0 the scan ends at step 2 instead)
           }
         } else {
 #pragma unroll 1
           for (int i = 0; i < m; i++) {
             const unsigned c = cidx[i];
+            const int k = (int)((c & LN_IDX) >> LN_IDX_SHIFT);
             double sum;
-            if (!(c & LN_DENSE) && finite) {
-              sum = d_mul(civ[i], sd[(c & LN_ROW) >> LN_ROW_SHIFT]);
-            } else if (!(c & LN_DENSE)) {
-              // non-finite x: the reference's full sum, with the column rebuilt from its (row, value)
-              // form -- a zero coefficient times a non-finite x[j] is a NaN term there, too
+            if (!(c & LN_GEN) && finite) {
+              sum = sd[k];
+            } else if (!(c & LN_GEN) || io.CIv) {
+              // non-finite x, or a non-unit coefficient that came in compressed form: the reference's full sum
+              // with the column rebuilt from its (row, value) form -- a zero coefficient times a non-finite
+              // x[j] is a NaN term there, too
+              double a;
+              int row;
+              if (c & LN_GEN) { a = MGQP_LDG(io.CIv + i); row = k; }
+              else { a = (k < N) ? 1.0 : ((k < 2 * N) ? -1.0 : 0.0); row = (k < N) ? k : ((k < 2 * N) ? k - N : 0); }
               sum = 0.0;
-              const int k = (int)((c & LN_ROW) >> LN_ROW_SHIFT);
-              const double a = civ[i];
 #pragma unroll
-              for (int j = 0; j < N; j++) sum = mad<FMA>((j == k) ? a : 0.0, x[j], sum);
+              for (int j = 0; j < N; j++) sum = mad<FMA>((j == row) ? a : 0.0, x[j], sum);
             } else {
               sum = 0.0;
 #pragma unroll
@@ -518,7 +709,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             }
             sum = d_add(sum, sci0[i]);
             d_acc_neg(psi, sum);
-            if (sum < ss && c < LN_EXCL) {
+            if (sum < ss && !(c & (LN_EXCL | LN_ACT))) {
               ss = sum;
               ip = i;
             }
@@ -527,7 +718,7 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
         const bool picked = ss < ss_in;  // ss only ever moves down, strictly
         if (picked) s_ip = ss;
         if (l1) {
-          if (d_abs(psi) <= thr) {
+          if (d_abs(psi) <= thr || !(ss < 0.0)) {  // (ss >= 0: step 2 would return the same f; skip the snapshot)
             done = true;
           } else {
 #pragma unroll
@@ -545,13 +736,17 @@ MGQP_DEV void gi_lane_solve(const LaneView& v, double* S, const LaneIO& io, int 
             done = true;
           } else {
             const unsigned c = cidx[ip];
-            if (c & LN_DENSE) {
+            const int k = (int)((c & LN_IDX) >> LN_IDX_SHIFT);
+            if ((c & LN_GEN) && !io.CIv) {
 #pragma unroll
               for (int j = 0; j < N; j++) np[j] = MGQP_LDG(io.CI + j * m + ip);
             } else {
-              const double a = civ[ip];
+              double a;
+              int row;
+              if (c & LN_GEN) { a = MGQP_LDG(io.CIv + ip); row = k; }
+              else { a = (k < N) ? 1.0 : ((k < 2 * N) ? -1.0 : 0.0); row = (k < N) ? k : ((k < 2 * N) ? k - N : 0); }
 #pragma unroll
-              for (int j = 0; j < N; j++) np[j] = (j == (int)((c & LN_ROW) >> LN_ROW_SHIFT)) ? a : 0.0;  // a == +-0 for an empty column
+              for (int j = 0; j < N; j++) np[j] = (j == row) ? a : 0.0;  // a == +0 for an empty column
             }
             su[iq] = 0.0;
             A[iq] = (signed char)ip;

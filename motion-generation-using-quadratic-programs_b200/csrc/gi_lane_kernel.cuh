@@ -1,14 +1,15 @@
-// Persistent kernel around gi_lane_solve: every WARP is an independent worker that pulls tiles of
+// Persistent kernel around gi_lane_tile: every WARP is an independent worker that pulls tiles of
 // 32 consecutive QPs from the atomic work queue; lane q of the warp owns QP q of the tile.
 //
-// There is no staging pass: every lane reads its own QP's G, g0, CI and ci0 straight from global
-// memory inside gi_lane_solve (consecutive 8-byte loads of one lane share 32-byte sectors, so HBM
-// sees every byte once and L1 serves the rest); only x goes through shared memory on the way out
-// so that its stores are coalesced.  (An L2 prefetch of the next tile was measured and removed: it
-// doubled the DRAM read traffic -- the lines were evicted before use -- without changing the run
-// time; profiles/r01_notes.md.)
+// The warp stages its tile cooperatively (gi_lane.cuh, phases A and B): consecutive lanes read consecutive
+// doubles of the tile's G, g0, CI and ci0 blocks, so every global load is coalesced and HBM sees every byte
+// once; x goes through shared memory on the way out so that its stores are coalesced, too.
 #pragma once
 #include "gi_lane.cuh"
+
+#ifndef MGQP_LANE_CTA_SYNC
+#define MGQP_LANE_CTA_SYNC 4
+#endif
 
 namespace mgqp {
 
@@ -53,28 +54,32 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
     batch = b < batch ? b : batch;
     tiles = (batch + 31) / 32;
   }
-  long long tile = next_tile(-1);
-  while (tile < tiles) {
+  // one tile: stage, solve, store
+  auto do_tile = [&](long long tile, long long tile_next) {
     const long long q0 = tile * 32;
     const long long rem = batch - q0;
     const int cnt = rem < 32 ? (int)rem : 32;
-    const long long tile_next = next_tile(tile);
-    const long long myq = q0 + (lane < cnt ? lane : 0);
-    LaneIO io;
-    io.G = P.in[0] + myq * P.stride[0];
-    io.g0 = P.in[1] + myq * P.stride[1];
-    io.CE = P.in[2] + myq * P.stride[2];
-    io.ce0 = P.in[3] + myq * P.stride[3];
-    io.CI = P.in[4] + myq * P.stride[4];
-    io.ci0 = P.in[5] + myq * P.stride[5];
+    LaneTileIO tio;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      tio.in[k] = P.in[k] + q0 * P.stride[k];
+      tio.stride[k] = P.stride[k];
+    }
     if (P.ci_val) {
-      io.CIv = P.ci_val + myq * P.s_ci_val;
-      io.CIr = P.ci_row + myq * P.s_ci_row;
+      tio.CIv = P.ci_val + q0 * P.s_ci_val;
+      tio.CIr = P.ci_row + q0 * P.s_ci_row;
+      tio.sCIv = P.s_ci_val;
+      tio.sCIr = P.s_ci_row;
+    }
+    tio.cnt = cnt;
+    if (tile_next < tiles) {  // pull the next tile's G / g0 towards L2 (phase A of the next round reads them)
+      tio.next_G = P.in[0] + tile_next * 32 * P.stride[0];
+      tio.next_g0 = P.in[1] + tile_next * 32 * P.stride[1];
     }
     double xo[N];
     double f;
     int status, iq, iters;
-    gi_lane_solve<N, FMA>(v, S, io, P.max_iter, xo, f, status, iq, iters);
+    gi_lane_tile<N, FMA>(v, ws, tio, P.max_iter, xo, f, status, iq, iters);
     __syncwarp();
 
     // ---- results: x through shared memory so that the global stores are coalesced
@@ -97,8 +102,44 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
       }
     }
     __syncwarp();
+  };
+
+#if MGQP_LANE_CTA_SYNC
+  // Synchronous rounds: groups of MGQP_LANE_CTA_SYNC warps start their tiles together (a named barrier per
+  // group), so that they walk through the same parts of the (large) code at about the same time and share
+  // instruction-cache lines.  Measured (profiles/r02_notes.md): with eight independent warps per SM a third of
+  // all stall samples were instruction-fetch misses.  The group's leader draws the tickets one round ahead, so
+  // that every warp knows its next tile while it works on the current one.
+  constexpr int GW = MGQP_LANE_CTA_SYNC;          // warps per group
+  __shared__ unsigned s_round_base[8];
+  const int grp = warp / GW, wig = warp - grp * GW;
+  const int grp_warps = (warps_per_cta - grp * GW) < GW ? (warps_per_cta - grp * GW) : GW;
+  auto grp_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(grp_warps * 32) : "memory"); };
+  auto draw = [&](long long round) {
+    if (wig == 0 && lane == 0)
+      s_round_base[grp] = P.ticket ? atomicAdd(P.ticket, (unsigned)grp_warps)
+                                   : (unsigned)((round * gridDim.x + blockIdx.x) * warps_per_cta + grp * GW);
+  };
+  grp_sync();
+  draw(0);
+  grp_sync();
+  long long cur = (long long)s_round_base[grp];
+  for (long long round = 0; cur < tiles; round++) {
+    grp_sync();
+    draw(round + 1);
+    grp_sync();
+    const long long nxt = (long long)s_round_base[grp];
+    if (cur + wig < tiles) do_tile(cur + wig, nxt + wig);
+    cur = nxt;
+  }
+#else
+  long long tile = next_tile(-1);
+  while (tile < tiles) {
+    const long long tile_next = next_tile(tile);
+    do_tile(tile, tile_next);
     tile = tile_next;
   }
+#endif
 }
 
 }  // namespace mgqp

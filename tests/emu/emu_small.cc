@@ -78,11 +78,45 @@ extern "C" int emu_solve_batch(int n, int p, int m, long long batch, const doubl
 #include "../../motion-generation-using-quadratic-programs_b200/csrc/gi_lane.cuh"
 
 namespace {
+struct LaneJob {
+  LaneView v;
+  double* ws;
+  LaneTileIO tio;
+  int max_iter, fma;
+  double* x; double* f; int* status; int* iq; int* A; int* iters;  // of the tile's first QP
+};
+
 template <int N>
-void lane_one(const LaneView& v, double* S, const LaneIO& io, int max_iter, int fma, double* x, double& f, int& st,
-              int& iq, int& it) {
-  if (fma) gi_lane_solve<N, true>(v, S, io, max_iter, x, f, st, iq, it);
-  else gi_lane_solve<N, false>(v, S, io, max_iter, x, f, st, iq, it);
+void lane_tile_n(LaneJob* j) {
+  const int lane = wp_lane();
+  double xo[8];
+  double fo;
+  int st, q, it;
+  if (j->fma) gi_lane_tile<N, true>(j->v, j->ws, j->tio, j->max_iter, xo, fo, st, q, it);
+  else gi_lane_tile<N, false>(j->v, j->ws, j->tio, j->max_iter, xo, fo, st, q, it);
+  if (lane >= j->tio.cnt) return;
+  const int n = j->v.n, p = j->v.p, m = j->v.m;
+  for (int i = 0; i < n; i++) j->x[lane * n + i] = xo[i];
+  j->f[lane] = fo;
+  j->status[lane] = st;
+  if (j->iq) j->iq[lane] = q;
+  if (j->iters) j->iters[lane] = it;
+  const signed char* Ab = reinterpret_cast<const signed char*>(j->ws + lane * j->v.stride + j->v.oByte) + j->v.bA;
+  if (j->A) for (int i = 0; i < p + m; i++) j->A[lane * (p + m) + i] = (i < q) ? (int)Ab[i] : 0x7fffffff;
+}
+
+void lane_tile_body(void* a) {
+  LaneJob* j = (LaneJob*)a;
+  switch (j->v.n) {
+    case 1: lane_tile_n<1>(j); break;
+    case 2: lane_tile_n<2>(j); break;
+    case 3: lane_tile_n<3>(j); break;
+    case 4: lane_tile_n<4>(j); break;
+    case 5: lane_tile_n<5>(j); break;
+    case 6: lane_tile_n<6>(j); break;
+    case 7: lane_tile_n<7>(j); break;
+    default: lane_tile_n<8>(j); break;
+  }
 }
 }  // namespace
 
@@ -100,6 +134,7 @@ extern "C" int emu_lane_solve_batch(int n, int p, int m, long long batch, const 
                                 nullptr, nullptr);
 }
 
+// The warp's 32 lanes run as fibers: the cooperative stage-in phases of gi_lane_tile synchronise the warp.
 extern "C" int emu_lane_solve_batch_c(int n, int p, int m, long long batch, const double* G, const double* g0,
                                       const double* CE, const double* ce0, const double* CI, const double* ci0,
                                       double* x, double* f, int* status, int* iq, int* A, int* iters, int max_iter,
@@ -107,35 +142,33 @@ extern "C" int emu_lane_solve_batch_c(int n, int p, int m, long long batch, cons
   if (n < 1 || n > 8 || m > 64 || p > n) return -2;
   const LaneView v = make_lane_view(n, p, m);
   if (max_iter <= 0) max_iter = 100 + 10 * (p + m);
-  std::vector<double> slot(v.stride);
-  for (long long b = 0; b < batch; b++) {
-    double* S = slot.data();
-    for (int i = 0; i < v.stride; i++) S[i] = -1e300;  // poison
-    LaneIO io{G + b * n * n, g0 + b * n, CE + b * n * p, ce0 + b * p, CI ? CI + b * n * m : nullptr, ci0 + b * m};
-    if (CIv) {
-      io.CIv = CIv + b * m;
-      io.CIr = CIr + b * m;
+  const long long tiles = (batch + 31) / 32;
+  std::atomic<long long> next(0);
+  auto work = [&]() {
+    std::vector<double> ws((size_t)32 * v.stride);
+    for (;;) {
+      const long long t = next.fetch_add(1);
+      if (t >= tiles) break;
+      const long long q0 = t * 32;
+      for (size_t i = 0; i < ws.size(); i++) ws[i] = -1e300;  // poison
+      LaneJob j;
+      j.v = v; j.ws = ws.data(); j.max_iter = max_iter; j.fma = fma;
+      const double* in[6] = {G + q0 * n * n, g0 + q0 * n, CE + q0 * n * p, ce0 + q0 * p,
+                             CI ? CI + q0 * (long long)n * m : nullptr, ci0 + q0 * m};
+      const long long st[6] = {(long long)n * n, n, (long long)n * p, p, (long long)n * m, m};
+      for (int k = 0; k < 6; k++) { j.tio.in[k] = in[k]; j.tio.stride[k] = st[k]; }
+      if (CIv) { j.tio.CIv = CIv + q0 * m; j.tio.CIr = CIr + q0 * m; j.tio.sCIv = m; j.tio.sCIr = m; }
+      j.tio.cnt = (int)((batch - q0) < 32 ? (batch - q0) : 32);
+      j.x = x + q0 * n; j.f = f + q0; j.status = status + q0;
+      j.iq = iq ? iq + q0 : nullptr;
+      j.A = A ? A + q0 * (p + m) : nullptr;
+      j.iters = iters ? iters + q0 : nullptr;
+      emu_run_warp(lane_tile_body, &j);
     }
-    double xo[8];
-    double fo;
-    int st, q, it;
-    switch (n) {
-      case 1: lane_one<1>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      case 2: lane_one<2>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      case 3: lane_one<3>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      case 4: lane_one<4>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      case 5: lane_one<5>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      case 6: lane_one<6>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      case 7: lane_one<7>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-      default: lane_one<8>(v, S, io, max_iter, fma, xo, fo, st, q, it); break;
-    }
-    for (int i = 0; i < n; i++) x[b * n + i] = xo[i];
-    f[b] = fo; status[b] = st;
-    if (iq) iq[b] = q;
-    if (iters) iters[b] = it;
-    const signed char* Ab = reinterpret_cast<const signed char*>(S + v.oByte) + v.bA;
-    if (A) for (int i = 0; i < p + m; i++) A[b * (p + m) + i] = (i < q) ? (int)Ab[i] : 0x7fffffff;
-  }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < 4; t++) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
   return 0;
 }
 

@@ -21,6 +21,7 @@
 #include <ucontext.h>
 
 #define MGQP_DEV static inline
+#define MGQP_MEMBER inline
 #define MGQP_DEV_NOINLINE static inline
 #define MGQP_UNROLL1
 #define MGQP_UNROLL2

@@ -129,3 +129,19 @@ def test_column_compressed_odd_shapes(emu_lib, restatement):
         b.CI[...] = 0.0
         np.put_along_axis(b.CI, rows[:, None, :], vals[:, None, :], axis=1)
         assert_bit_identical(lane_solve(emu_lib, b, compressed=_compress(b.CI)), _oracle(restatement, b), f"R{n}_{p}_{m}")
+
+
+def test_dense_input_unit_nonunit_and_signed_zero_columns(emu_lib, restatement):
+    """Phase B sorts the dense CI block into +-e_k bytes, empty columns and exact-path (GEN) columns:
+    non-unit bounds, two-nonzero columns and -0.0 entries must all come out bit-identical."""
+    for n, p, m in [(7, 1, 42), (5, 0, 13), (8, 2, 64), (2, 0, 40), (7, 7, 3)]:
+        b = workloads.make_random(257, n, p, m, seed=31 * n + m)
+        rng = np.random.default_rng(n + m)
+        rows = rng.integers(0, n, size=(b.batch, m))
+        vals = rng.choice([-1.0, 1.0, 1.0, -1.0, 0.5, -2.5, 0.0], size=(b.batch, m))
+        b.CI[...] = 0.0
+        np.put_along_axis(b.CI, rows[:, None, :], vals[:, None, :], axis=1)
+        b.CI[3::7, 0, m // 2] = -0.0                      # a -0.0 entry sends its column down the exact path
+        b.CI[5::11, n - 1, 0] += 0.25                     # a second nonzero / a non-unit value
+        b.CI[::2, :, :] = np.where(b.CI[::2] == 0.5, 1.0, b.CI[::2])   # every other QP: units and zeros only
+        assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), f"U{n}_{p}_{m}")
