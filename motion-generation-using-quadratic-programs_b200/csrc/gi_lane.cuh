@@ -53,6 +53,7 @@
 #define MGQP_LDG2(p, a, b) do { (a) = (p)[0]; (b) = (p)[1]; } while (0)
 #define MGQP_LDG2_STREAM(p, a, b) MGQP_LDG2(p, a, b)
 #define MGQP_PREFETCH_L2(p) do { } while (0)
+#define MGQP_PREFETCH_L2_KEEP(p) do { } while (0)
 #define MGQP_CP8(dst, src) (*(dst) = *(src))
 #define MGQP_CP_WAIT() do { } while (0)
 #define MGQP_OPAQUE_PTR(p) do { } while (0)
@@ -61,6 +62,7 @@
 // instead of being re-associated into 64-bit index arithmetic
 #define MGQP_OPAQUE_PTR(p) asm volatile("" : "+l"(p))
 #define MGQP_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define MGQP_PREFETCH_L2_KEEP(p) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p))
 #define MGQP_LDG(p) __ldg(p)
 #define MGQP_LDG2(p, a, b) do { const double2 v2_ = __ldg(reinterpret_cast<const double2*>(p)); (a) = v2_.x; (b) = v2_.y; } while (0)
 #define MGQP_LDG2_STREAM(p, a, b) asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p))
@@ -69,8 +71,13 @@
 #define MGQP_CP_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #endif
 
+#ifdef MGQP_LANE_KEEP
+#define MGQP_PREFETCH_NEXT(p) MGQP_PREFETCH_L2_KEEP(p)
+#else
+#define MGQP_PREFETCH_NEXT(p) MGQP_PREFETCH_L2(p)
+#endif
 #ifndef MGQP_LANE_K
-#define MGQP_LANE_K 2
+#define MGQP_LANE_K 1
 #endif
 
 namespace mgqp {
@@ -216,10 +223,10 @@ MGQP_DEV void ln_prefetch_next(const LaneTileIO& t, int n) {
   const int lane = wp_lane();
   const char* p = reinterpret_cast<const char*>(t.next_G);
 #pragma unroll 1
-  for (int o = lane * 128; o < 32 * n * n * 8; o += 32 * 128) MGQP_PREFETCH_L2(p + o);
+  for (int o = lane * 128; o < 32 * n * n * 8; o += 32 * 128) MGQP_PREFETCH_NEXT(p + o);
   const char* p0 = reinterpret_cast<const char*>(t.next_g0);
 #pragma unroll 1
-  for (int o = lane * 128; o < 32 * n * 8; o += 32 * 128) MGQP_PREFETCH_L2(p0 + o);
+  for (int o = lane * 128; o < 32 * n * 8; o += 32 * 128) MGQP_PREFETCH_NEXT(p0 + o);
 }
 
 // pull the tile's CI / ci0 blocks towards L2 while phases A and S run (phase B reads them)
@@ -294,17 +301,18 @@ MGQP_DEV void ln_stage_G(const LaneView& v, double* __restrict__ ws, const LaneT
   MGQP_CP_WAIT();
 }
 
-// One inequality column -> its byte.  `acc` counts 64 per nonzero entry and adds 8 * row; `val` is the ordered
-// sum of the column, which IS the single nonzero bit for bit when there is exactly one (v + (+-0.0) == v).
+// One inequality column -> its byte.  `mask` has bit j set iff entry j is nonzero; `val` is the ordered sum of
+// the column, which IS the single nonzero bit for bit when there is exactly one (v + (+-0.0) == v).
 // (-0.0 counts as a zero: every use of a coefficient is a product added to a sum that starts at +0.0, where
 // the sign of a zero coefficient cannot show.)
 template <int N>
-MGQP_DEV unsigned ln_column_byte(unsigned acc, double val) {
-  unsigned byte = LN_GEN | (acc & 0x38u);                            // one nonzero, not a unit: exact path
-  if (val == 1.0) byte = acc & 0x38u;                                // +x_k
-  if (val == -1.0) byte = (acc & 0x38u) + (unsigned)(8 * N);         // -x_k
-  if (acc >= 128u) byte = LN_GEN;                                    // two or more nonzeros
-  if (acc < 64u) byte = (unsigned)(2 * N) << LN_IDX_SHIFT;           // empty column: contributes +0.0
+MGQP_DEV unsigned ln_column_byte(unsigned mask, double val) {
+  const unsigned row8 = (unsigned)(wp_ffs(mask) - 1) << LN_IDX_SHIFT;  // mask == 0: overwritten below
+  unsigned byte = LN_GEN | row8;                                     // one nonzero, not a unit: exact path
+  if (val == 1.0) byte = row8;                                       // +x_k
+  if (val == -1.0) byte = row8 + (unsigned)(8 * N);                  // -x_k
+  if (mask & (mask - 1)) byte = LN_GEN;                              // two or more nonzeros
+  if (mask == 0) byte = (unsigned)(2 * N) << LN_IDX_SHIFT;           // empty column: contributes +0.0
   return byte;
 }
 
@@ -336,38 +344,47 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
     int doff = q * v.stride + c;
     const int dstep = dq * v.stride + dc, dwrap = v.stride - m;
     const unsigned de = 32 + dq * (N - 1) * m, ewrap = (N - 1) * m;
-    constexpr int K = MGQP_LANE_K;               // columns per trip: K*N loads in flight per lane
-#pragma unroll 1
-    for (int r0 = 0; r0 < m; r0 += K) {
-      double b[K][N];
-      int c_[K], doff_[K];
-      unsigned t_[K];
+    constexpr int K = MGQP_LANE_K;               // columns per trip; two trips (2*K*N loads) in flight per lane
+    struct Trip { double b[K][N]; int c[K], doff[K]; unsigned t[K]; };
+    auto load = [&](Trip& T, int r0) {
 #pragma unroll
       for (int u = 0; u < K; u++) {
         if (r0 + u < m) {  // warp-uniform
 #pragma unroll
-          for (int j = 0; j < N; j++) b[u][j] = MGQP_LDG(rowp[j] + e);
-          c_[u] = c; doff_[u] = doff; t_[u] = tt;
+          for (int j = 0; j < N; j++) T.b[u][j] = MGQP_LDG(rowp[j] + e);
+          T.c[u] = c; T.doff[u] = doff; T.t[u] = tt;
           tt += 32; c += dc; e += de; doff += dstep;
           if (c >= m) { c -= m; e += ewrap; doff += dwrap; }
         }
       }
+    };
+    auto sort = [&](const Trip& T, int r0) {
 #pragma unroll
       for (int u = 0; u < K; u++) {
         if (r0 + u < m) {
-          double val = b[u][0];
-          unsigned acc = (b[u][0] != 0.0) ? 64u : 0u;  // NaN counts as nonzero
+          double val = T.b[u][0];
+          unsigned mask = 0;
+          d_or_if_nonzero(mask, T.b[u][0], 1u);  // NaN counts as nonzero
 #pragma unroll
           for (int j = 1; j < N; j++) {
-            val = d_add(val, b[u][j]);
-            if (b[u][j] != 0.0) acc += 64u + 8u * j;
+            val = d_add(val, T.b[u][j]);
+            d_or_if_nonzero(mask, T.b[u][j], 1u << j);
           }
-          const unsigned byte = ln_column_byte<N>(acc, val);
-          MGQP_CP8(dci0 + doff_[u], ci0 + t_[u]);
-          bytes[8 * doff_[u] - 7 * c_[u]] = (unsigned char)byte;
-          if (byte & LN_GEN) gen[8 * (doff_[u] - c_[u])] = 1;
+          const unsigned byte = ln_column_byte<N>(mask, val);
+          MGQP_CP8(dci0 + T.doff[u], ci0 + T.t[u]);
+          bytes[8 * T.doff[u] - 7 * T.c[u]] = (unsigned char)byte;
+          if (byte & LN_GEN) gen[8 * (T.doff[u] - T.c[u])] = 1;
         }
       }
+    };
+    Trip A, B;
+    load(A, 0);
+#pragma unroll 1
+    for (int r0 = 0; r0 < m; r0 += 2 * K) {
+      load(B, r0 + K);
+      sort(A, r0);
+      load(A, r0 + 2 * K);
+      sort(B, r0 + K);
     }
     MGQP_CP_WAIT();
     return;
@@ -397,7 +414,7 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
         const double a = MGQP_LDG(t.CIv + so);
         unsigned row = MGQP_LDG(t.CIr + ro);
         row = row < (unsigned)N ? row : (unsigned)(N - 1);  // a corrupt batch stays inside the table
-        byte = ln_column_byte<N>((a != 0.0 ? 64u : 0u) + 8u * row, a);
+        byte = ln_column_byte<N>(a != 0.0 ? (1u << row) : 0u, a);
       }
       finish(w.q, w.k, w.doff, w.soff, byte);
       const int k0 = w.k;
@@ -417,14 +434,15 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
       if (w.q < t.cnt) {
         const double* src = CI + co;
         double val = MGQP_LDG(src);
-        unsigned acc = (val != 0.0) ? 64u : 0u;
+        unsigned mask = 0;
+        d_or_if_nonzero(mask, val, 1u);
 #pragma unroll
         for (int j = 1; j < N; j++) {
           const double bj = MGQP_LDG(src + j * m);
           val = d_add(val, bj);
-          if (bj != 0.0) acc += 64u + 8u * j;
+          d_or_if_nonzero(mask, bj, 1u << j);
         }
-        byte = ln_column_byte<N>(acc, val);
+        byte = ln_column_byte<N>(mask, val);
       }
       finish(w.q, w.k, w.doff, w.soff, byte);
       const int k0 = w.k;
@@ -658,15 +676,32 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
           // every column is +-e_k or empty: s_i = +-x[k] + ci0_i equals the reference's N-term sum wherever a
           // comparison can see it (the two can differ in the sign of a zero only)
           const char* tab = reinterpret_cast<const char*>(sd);
-#pragma unroll 6
-          for (int i = 0; i < m; i++) {
-            const unsigned c = cidx[i];
-            const double sum = d_add(*reinterpret_cast<const double*>(tab + (c & LN_IDX)), sci0[i]);
-            if (sum < ss && !(c & (LN_EXCL | LN_ACT))) {
-              ss = sum;
-              ip = i;
-            }
+          // three interleaved searches (columns i = 0, 1, 2 mod 3), merged below: the compare-select chain of a
+          // single running minimum is one long dependency, three of them overlap
+          double s0 = ss, s1 = ss, s2 = ss;
+          int i0 = ip, i1 = ip, i2 = ip;
+          int i = 0;
+#pragma unroll 2
+          for (; i + 2 < m; i += 3) {
+            const unsigned ca = cidx[i], cb = cidx[i + 1], cc = cidx[i + 2];
+            const double sa = d_add(*reinterpret_cast<const double*>(tab + (ca & LN_IDX)), sci0[i]);
+            const double sb = d_add(*reinterpret_cast<const double*>(tab + (cb & LN_IDX)), sci0[i + 1]);
+            const double sc = d_add(*reinterpret_cast<const double*>(tab + (cc & LN_IDX)), sci0[i + 2]);
+            if (sa < s0 && !(ca & (LN_EXCL | LN_ACT))) { s0 = sa; i0 = i; }
+            if (sb < s1 && !(cb & (LN_EXCL | LN_ACT))) { s1 = sb; i1 = i + 1; }
+            if (sc < s2 && !(cc & (LN_EXCL | LN_ACT))) { s2 = sc; i2 = i + 2; }
           }
+          for (; i < m; i++) {
+            const unsigned ca = cidx[i];
+            const double sa = d_add(*reinterpret_cast<const double*>(tab + (ca & LN_IDX)), sci0[i]);
+            if (sa < s0 && !(ca & (LN_EXCL | LN_ACT))) { s0 = sa; i0 = i; }
+          }
+          // the reference keeps the FIRST index of the strict minimum: smaller value wins, equal values -> smaller
+          // index (a search that found nothing still holds the incoming (ss, ip) and loses every comparison)
+          if (s1 < s0 || (s1 == s0 && s1 < ss && i1 < i0)) { s0 = s1; i0 = i1; }
+          if (s2 < s0 || (s2 == s0 && s2 < ss && i2 < i0)) { s0 = s2; i0 = i2; }
+          ss = s0;
+          ip = i0;
           // psi = sum_i min(0, s_i) is only ever compared with thr (step 1: |psi| <= thr -> return f).  It is a
           // sum of negative terms, so psi <= each of them (rounding is monotonic), in particular psi <= ss:
           // whenever ss < -thr the test fails without psi being known.  And with ss >= 0 the outcome does not

@@ -196,6 +196,8 @@ MGQP_DEV double d_sqrt(double a) { return sqrt(a); }
 MGQP_DEV double d_fma(double a, double b, double c) { return fma(a, b, c); }
 MGQP_DEV double d_abs(double a) { return fabs(a); }
 MGQP_DEV void d_acc_neg(double& acc, double a) { if (a < 0.0) acc = acc + a; }
+MGQP_DEV void d_or_if_nonzero(unsigned& mask, double a, unsigned bit) { if (a != 0.0) mask |= bit; }
+MGQP_DEV int i_popc(unsigned v) { return __builtin_popcount(v); }
 MGQP_DEV double d_inf() { return INFINITY; }
 MGQP_DEV bool d_is_pos_zero(double a) { return emu_bits(a) == 0; }
 MGQP_DEV int wp_ffs(unsigned v) { return __builtin_ffs((int)v); }

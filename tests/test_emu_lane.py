@@ -145,3 +145,13 @@ def test_dense_input_unit_nonunit_and_signed_zero_columns(emu_lib, restatement):
         b.CI[5::11, n - 1, 0] += 0.25                     # a second nonzero / a non-unit value
         b.CI[::2, :, :] = np.where(b.CI[::2] == 0.5, 1.0, b.CI[::2])   # every other QP: units and zeros only
         assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), f"U{n}_{p}_{m}")
+
+
+def test_scan_ties_keep_the_first_index(emu_lib, restatement):
+    """Duplicated bound columns give exactly equal s_i: the reference keeps the first index of the minimum."""
+    b = workloads.make("C2", 1500)
+    for src, dst in [(5, 20), (5, 33), (1, 2), (40, 3), (14, 41)]:
+        b.CI[:, :, dst] = b.CI[:, :, src]
+        b.ci0[:, dst] = b.ci0[:, src]
+    b.ci0[:, [5, 20, 33, 1, 2]] -= 1.5      # make the duplicated bounds bite
+    assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), "ties")
