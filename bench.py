@@ -35,13 +35,22 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-QPS_PER_GPU = {"C2": 1_000_000, "C5": 1_000_000, "C3": 100_000, "C4": 592, "S0": 400_000, "S2": 400_000}
-CPU_SAMPLE = {"C2": 200_000, "C5": 200_000, "C3": 60_000, "C4": 16, "S0": 60_000, "S2": 100_000}
+QPS_PER_GPU = {"C2": 1_000_000, "C5": 1_000_000, "C5D": 1_000_000, "C3": 100_000, "C4": 592, "S0": 400_000,
+               "S2": 400_000}
+# CPU baseline samples: (QPs solved on all host threads, QPs solved on one thread) -- about a second or two each
+CPU_SAMPLE = {"C2": (200_000, 20_000), "C5": (200_000, 20_000), "C5D": (200_000, 20_000), "C3": (60_000, 6_000),
+              "C4": (16, 1), "S0": (60_000, 6_000), "S2": (100_000, 10_000)}
+# the sub-records bench.py appends to the headline line at N = 1: (workload, QPs per step, steps)
+EXTRA_CONFIGS = [("C5", 1_000_000, 5), ("C5D", 1_000_000, 5), ("C3", 100_000, 5), ("S0", 400_000, 5),
+                 ("S2", 400_000, 5)]
+C4_FULL = 10_000          # BASELINE.json configs[3]: 10k horizon-stacked QPs (generated on the device)
+C5_SHARDED_TOTAL = 10_000_000  # BASELINE.json configs[4]: 10M-QP sweep, strong-scaled over the ranks
 
 
 CONFIG_NOTE = {
     "C2": "BASELINE.json configs[1]: 1M independent random 7-DoF mgqp QPs",
     "C5": "BASELINE.json configs[4] shape: scenario sweep, ~10 % infeasible",
+    "C5D": "configs[4] with a second equality: ~10 % infeasible, ~1 % linearly dependent equalities (SURVEY.md 8d)",
     "C3": "BASELINE.json configs[2]: task-space QPs with slacks",
     "C4": "BASELINE.json configs[3]: horizon-stacked MPC QPs, 7 DoF x 50 steps",
     "S0": "as-shipped mgqp level 0 (src/mgqp.cpp:1076-1143)",
@@ -132,13 +141,250 @@ def cpu_reference_rate(b, threads: int):
     return b.batch / (time.perf_counter() - t0), "port"
 
 
+def cpu_contenders(b, name: str):
+    """both CPU contenders -- (i) the shipped libquadprog.a (GCC 5.4 -O0, oracle/_ref) and
+    (ii) the -O2 restatement (oracle/gi_oracle.c) -- each on all host threads and on one thread, on bounded
+    samples of batch b.  QPs/s; None where oracle/_ref was not built."""
+    from oracle import oracle_py
+    nthreads = host_threads()
+    n_all, n_one = CPU_SAMPLE[name]
+    n_all, n_one = min(n_all, b.batch), min(n_one, b.batch)
+    out = {"cores": nthreads, "sample_all_threads": n_all, "sample_one_thread": n_one, "unit": "QP/s"}
+    ref, rest = oracle_py.reference(), oracle_py.restatement()
+    for key, solver in (("shipped_O0", ref), ("restatement_O2", rest)):
+        if solver is None:
+            out[key] = None
+            continue
+        rec = {}
+        for label, cnt, thr in (("all_threads", n_all, nthreads), ("one_thread", n_one, 1)):
+            sb = b.slice(0, cnt)
+            t0 = time.perf_counter()
+            solver.solve_batch(sb.n, sb.p, sb.m, *sb.fields(), threads=thr)
+            rec[label] = cnt / (time.perf_counter() - t0)
+        out[key] = rec
+    return out
+
+
+def parity_vs_oracle(b, got_x, got_f, got_status, ns):
+    from oracle import oracle_py
+    sb = b.slice(0, ns)
+    chk = oracle_py.restatement().solve_batch(sb.n, sb.p, sb.m, *sb.fields(), max_iter=100 + 10 * (sb.p + sb.m),
+                                              threads=host_threads())
+    return {"sample": int(ns), "status_equal": bool(np.array_equal(got_status[:ns], chk["status"])),
+            "x_bit_identical": bool(np.array_equal(got_x[:ns], chk["x"], equal_nan=True)),
+            "f_bit_identical": bool(np.array_equal(got_f[:ns], chk["f"], equal_nan=True))}
+
+
+def timed_launches(mgqp_b200, dev_in, steps, warmup, flags, out=None, **kw):
+    """(mean ms per launch, result) of the device-resident solver, CUDA events on torch's current stream."""
+    import torch
+    out = mgqp_b200.solve_quadprog_batched(*dev_in, flags=flags, out=out, **kw)
+    for _ in range(max(0, warmup - 1)):
+        mgqp_b200.solve_quadprog_batched(*dev_in, flags=flags, out=out, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        mgqp_b200.solve_quadprog_batched(*dev_in, flags=flags, out=out, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def kernel_name(mgqp_b200, n, p, m):
+    gw, warps, smem = mgqp_b200.plan(n, p, m)
+    k = {1: "gi_lane_kernel<%d> (one QP per lane)" % n, 0: "gi_large_kernel (one QP per CTA)"}.get(
+        gw, "gi_small_kernel<%d> (%d lanes per QP)" % (gw, gw))
+    return f"{k}, {warps} warps/CTA, {smem} B smem/CTA"
+
+
+def extra_config_record(mgqp_b200, name, B, steps, dev, peak):
+    """One sub-record: a BASELINE config other than the headline, device-resident, with parity and CPU baselines."""
+    import torch
+    from mgqp_b200 import workloads
+    b = workloads.make(name, B)
+    n, p, m = b.n, b.p, b.m
+    dev_in = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in b.fields()]
+    ms, out = timed_launches(mgqp_b200, dev_in, steps, 3, 0)
+    status = out.status.cpu().numpy()
+    ns = min(B, CPU_SAMPLE[name][0])
+    bytes_per_qp = mgqp_b200.algorithmic_bytes(n, p, m)
+    achieved = B * bytes_per_qp / (ms / 1e3) / 1e9
+    host_np = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in b.fields()]
+    res = mgqp_b200.solve_quadprog_batched_host(*host_np, device=dev.index or 0)  # warm (staging arenas)
+    t0 = time.perf_counter()
+    res = mgqp_b200.solve_quadprog_batched_host(*host_np, device=dev.index or 0, out=res)
+    e2e_s = time.perf_counter() - t0
+    h2d, d2h = mgqp_b200.last_transfer_bytes()
+    rec = {"workload": f"{name}: {B} QPs, n={n} p={p} m={m} ({CONFIG_NOTE[name]})", "value": B / (ms / 1e3),
+           "unit": "QP/s", "ms_per_step": ms, "steps": steps, "kernel": kernel_name(mgqp_b200, n, p, m),
+           "status_counts": np.bincount(status & 15, minlength=5).tolist(),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "bytes_per_qp": bytes_per_qp},
+           "e2e": {"value": B / e2e_s, "unit": "QP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "steps": 1, "note": "second call of solve_quadprog_batched_host on pinned host arrays",
+                   "matches_device_leg": bool(np.array_equal(res.status, status))},
+           "parity_check": parity_vs_oracle(b, out.x.cpu().numpy(), out.f.cpu().numpy(), status, ns),
+           "cpu_baseline": cpu_contenders(b, name)}
+    del dev_in, out
+    torch.cuda.empty_cache()
+    return rec
+
+
+def c4_record(mgqp_b200, dev, peak, B):
+    """BASELINE.json configs[3] at its stated size: B horizon-stacked QPs (n = 350, m = 2100) generated on the
+    device (69 GB at 10k QPs).  The HBM fraction uses SURVEY.md 8(d)'s one-read bytes; the CI re-reads the
+    algorithm itself performs (one pass over CI per violated-constraint scan) are reported next to it, never
+    folded into it."""
+    import torch
+    from mgqp_b200 import workloads
+    n, p, m = workloads.SHAPES["C4"]
+    free, _ = torch.cuda.mem_get_info(dev)
+    per_qp = 8 * (n * n + n + n * m + m)
+    B = int(min(B, (free * 0.8 - (6 << 30)) // (per_qp + 8 * n * n)))  # G is built from an n*n temporary
+    t = workloads.make_c4_device(B, dev)
+    torch.cuda.synchronize()
+    ms, out = timed_launches(mgqp_b200, t, 1, 1, 0, want_active_set=True)
+    status = out.status.cpu().numpy()
+    iters = out.iters.double()
+    ns = 8
+    sample = workloads.QPBatch("C4", n, p, m, *[a[:ns].cpu().numpy() for a in t])
+    bytes_per_qp = mgqp_b200.algorithmic_bytes(n, p, m)
+    achieved = B * bytes_per_qp / (ms / 1e3) / 1e9
+    scans = float(iters.mean().item()) + 1.0
+    x = out.x
+    # size-independent property at full size: every OK answer is primal feasible to 1e-9 (relative to the bound)
+    CI, ci0 = t[4], t[5]
+    viol = 0
+    for lo in range(0, B, 256):
+        hi = min(B, lo + 256)
+        s = torch.einsum("bnm,bn->bm", CI[lo:hi], x[lo:hi]) + ci0[lo:hi]
+        ok = (out.status[lo:hi] == 0)
+        viol += int(((s < -1e-9 * (1.0 + ci0[lo:hi].abs())).any(dim=1) & ok).sum().item())
+    rec = {"workload": f"C4: {B} QPs, n={n} p={p} m={m} ({CONFIG_NOTE['C4']}); generated on the device, "
+                       f"{B * per_qp / 1e9:.1f} GB resident", "value": B / (ms / 1e3), "unit": "QP/s",
+           "ms_per_step": ms, "steps": 1, "kernel": kernel_name(mgqp_b200, n, p, m),
+           "status_counts": np.bincount(status & 15, minlength=5).tolist(),
+           "mean_steps_per_qp": float(iters.mean().item()),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "bytes_per_qp": bytes_per_qp,
+                        "ci_reread_bytes_per_qp": int((scans - 1.0) * 8 * n * m),
+                        "note": "frac = SURVEY.md 8(d) one-read bytes / time; the algorithm re-reads CI (8nm bytes) in "
+                                "each of its scans: that traffic is reported separately, not as useful work"},
+           "primal_infeasible_answers": viol,
+           "parity_check": parity_vs_oracle(sample, x[:ns].cpu().numpy(), out.f[:ns].cpu().numpy(), status, ns),
+           "cpu_baseline": cpu_contenders(sample, "C4")}
+    # SURVEY.md 8d for the horizon-stacked shape: the dense factorisation part on its own (Cholesky n^3/3 +
+    # triangular inverse n^3/3 + solve 2n^2 flops): same G, g0 with no constraints, against an fp64 GEMM peak
+    # measured here with torch.matmul.
+    Bd = min(B, 1184)
+    z = lambda *sh: torch.zeros(sh, dtype=torch.float64, device=dev)
+    bare = [t[0][:Bd], t[1][:Bd], z(Bd, n, 0), z(Bd, 0), z(Bd, n, 0), z(Bd, 0)]
+    dense_ms, _ = timed_launches(mgqp_b200, bare, 2, 1, 16)
+    flops = (2.0 * n ** 3 / 3.0 + 2.0 * n * n) * Bd
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    torch.matmul(a, a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        torch.matmul(a, a)
+    e1.record()
+    torch.cuda.synchronize()
+    p64 = 3 * 2.0 * 4096 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
+    rec["dense_part"] = {"what": f"set-up only (Cholesky, J = L^-T, x0) of {Bd} QPs: same G, g0, p = m = 0",
+                         "ms": dense_ms, "tflops": flops / (dense_ms / 1e3) / 1e12, "peak_tflops": p64,
+                         "peak_source": "torch.matmul fp64 4096^3 on this GPU",
+                         "frac": flops / (dense_ms / 1e3) / 1e12 / p64}
+    del t, out, bare
+    torch.cuda.empty_cache()
+    return rec
+
+
+def c1_latency_record(mgqp_b200):
+    """BASELINE.json configs[0]: ONE QP per control cycle through the C++ drop-in solve_quadprog() (the symbol
+    src/mgqp.cpp:708 links against), as-shipped shapes S0 and S2; median wall-clock microseconds per call next to
+    the CPU solvers' per-QP time on one thread."""
+    import ctypes as C
+    from mgqp_b200 import workloads
+    from oracle import oracle_py
+    L = mgqp_b200.lib()
+    dp = C.POINTER(C.c_double)
+    L.mgqp_dropin_latency.restype = C.c_int
+    L.mgqp_dropin_latency.argtypes = [C.c_int32] * 3 + [dp] * 6 + [C.c_int, dp, dp, dp]
+    rec = {}
+    for name in ("S0", "S2"):
+        b = workloads.make(name, 256)
+        reps = 300
+        us = np.zeros(reps)
+        xs = np.zeros(b.n)
+        f = C.c_double(0.0)
+        a = [np.ascontiguousarray(v[3]) for v in b.fields()]  # QP 3 of the batch
+        rc = L.mgqp_dropin_latency(b.n, b.p, b.m, *[v.ctypes.data_as(dp) for v in a], reps, us.ctypes.data_as(dp),
+                                   xs.ctypes.data_as(dp), C.byref(f))
+        one = oracle_py.restatement().solve_one(*a)
+        cpu = {}
+        ref, rest = oracle_py.reference(), oracle_py.restatement()
+        for key, solver in (("shipped_O0_us_per_qp", ref), ("restatement_O2_us_per_qp", rest)):
+            if solver is None:
+                cpu[key] = None
+                continue
+            t0 = time.perf_counter()
+            solver.solve_batch(b.n, b.p, b.m, *b.fields(), threads=1)
+            cpu[key] = 1e6 * (time.perf_counter() - t0) / b.batch
+        rec[name] = {"shape": f"n={b.n} p={b.p} m={b.m}", "calls": reps, "rc": int(rc),
+                     "median_us": float(np.median(us[20:])), "p10_us": float(np.percentile(us[20:], 10)),
+                     "p90_us": float(np.percentile(us[20:], 90)), "first_call_us": float(us[0]),
+                     "bit_identical_to_oracle": bool(np.array_equal(xs, one["x"]) and f.value == one["f"]),
+                     "cpu_one_thread": cpu}
+    rec["what"] = ("C++ drop-in solve_quadprog(ArrayHH...) at B = 1: host copy into pinned staging, one H2D copy, one "
+                   "kernel launch, one D2H copy, one stream synchronisation per call")
+    return rec
+
+
+def c5_sharded_record(mgqp_b200, dev, rank, world, dist):
+    """BASELINE.json configs[4]: a 10M-QP sweep with mixed feasible / infeasible instances, STRONG-scaled: the same
+    10M QPs are split by QP index over the ranks (one GPU each, no data-path collective).  Every rank's shard is a
+    1M-QP seeded batch repeated on the device; time = max over ranks."""
+    import torch
+    from mgqp_b200 import sharding, workloads
+    lo, hi = sharding.shard_range(C5_SHARDED_TOTAL, rank, world)
+    mine = hi - lo
+    base = workloads.make("C5", min(1_000_000, mine), seed=sharding.rank_seed(1234 + 5, rank))
+    reps = -(-mine // base.batch)
+    dev_in = [torch.from_numpy(np.ascontiguousarray(a)).to(dev).repeat((reps,) + (1,) * (a.ndim - 1))[:mine]
+              for a in base.fields()]
+    out = mgqp_b200.solve_quadprog_batched(*dev_in)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mgqp_b200.solve_quadprog_batched(*dev_in, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    my_ms = e0.elapsed_time(e1)
+    ms = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    counts = torch.bincount(out.status.long() & 15, minlength=5).double()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts)
+    value = sharding.whole_job_rate(mine, my_ms / 1e3)  # all ranks' QPs / max-over-ranks time
+    del dev_in, out
+    torch.cuda.empty_cache()
+    return {"workload": f"C5: {C5_SHARDED_TOTAL} QPs in total, split by QP index over {world} rank(s)",
+            "scaling": "strong", "value": value, "unit": "QP/s", "ms": float(ms.item()), "qps_per_rank": int(mine),
+            "status_counts": [int(v) for v in counts.tolist()]}
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     from mgqp_b200 import workloads
     name = args.workload
     nthreads = host_threads()
-    sample = CPU_SAMPLE[name]
+    sample = CPU_SAMPLE[name][0]
     b = workloads.make(name, sample)
     n, p, m = b.n, b.p, b.m
     rates = []
@@ -215,16 +461,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     launches = mgqp_b200.kernel_launch_count() - l0
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * B * args.steps / (total_ms / 1e3)
+    value = sharding.whole_job_rate(B * args.steps, total_ms / 1e3)  # all ranks' QPs / max-over-ranks device time
+    ms_per_step = world * B * 1e3 / value
     status = out.status.cpu().numpy()
 
     # ---- end-to-end leg: host (pinned) buffers through the plugin call, copies inside the timing
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps or args.steps)
     host_np = [t.numpy() for t in host_pinned]
     res = mgqp_b200.QPResult(torch.empty((B, n), dtype=torch.float64).pin_memory().numpy(),
                              torch.empty((B,), dtype=torch.float64).pin_memory().numpy(),
@@ -237,10 +479,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()  # sampled over both timed regions (device-resident leg and e2e leg)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
+    e2e_value = sharding.whole_job_rate(B * e2e_steps, e2e_s)
     # bytes that actually crossed the link in the last call (the library counts its own copies): where a
     # chunk's CI is a set of bounds it travels column-compressed (m*9 bytes, mgqp_batch::CI_val) instead
     # of as the dense n*m*8-byte block the caller handed over
@@ -248,14 +487,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     host_bytes = sum(a.nbytes for a in host_np)
     e2e_same = bool(np.array_equal(res.status, status) and np.array_equal(res.x, out.x.cpu().numpy()))
 
+    peak, peak_src = peaks()
+    # ---- BASELINE.json configs[4] at its stated size, strong-scaled over the ranks (every rank takes part)
+    c5s = None
+    if not args.no_extras and name == "C2":
+        del dev_in
+        torch.cuda.empty_cache()
+        c5s = c5_sharded_record(mgqp_b200, dev, rank, world, dist)
+        dev_in = None
     if rank != 0:
         return
     # ---- parity spot check + CPU baseline on a bounded sample of the same inputs (rank 0, N=1 only)
     line_cpu = None
     parity = None
+    contenders = None
     if world == 1 and not args.no_cpu:
-        from oracle import oracle_py
-        ns = min(B, CPU_SAMPLE[name])
+        ns = min(B, CPU_SAMPLE[name][0])
         sb = b.slice(0, ns)
         nthreads = host_threads()
         rate, kind = cpu_reference_rate(sb, nthreads)
@@ -263,27 +510,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "sample": f"first {ns} QPs of the step's batch, {nthreads} host threads, "
                               + ("shipped libquadprog.a (GCC 5.4 -O0) via oracle/_ref" if kind == "reference"
                                  else "oracle/gi_oracle.c -O2")}
-        chk = oracle_py.restatement().solve_batch(n, p, m, *sb.fields(), max_iter=100 + 10 * (p + m), threads=nthreads)
-        xg = out.x[:ns].cpu().numpy()
-        fg = out.f[:ns].cpu().numpy()
-        parity = {"sample": ns, "status_equal": bool(np.array_equal(status[:ns], chk["status"])),
-                  "x_bit_identical": bool(np.array_equal(xg, chk["x"])),
-                  "f_bit_identical": bool(np.array_equal(fg, chk["f"], equal_nan=True))}
-    peak, peak_src = peaks()
+        contenders = cpu_contenders(b, name)
+        parity = parity_vs_oracle(b, out.x[:ns].cpu().numpy(), out.f[:ns].cpu().numpy(), status, ns)
     kern_ms = float(np.mean(step_ms))  # one launch per step: the step IS the kernel (+ a 4-byte memset)
-    gw, warps, smem = mgqp_b200.plan(n, p, m)
-    roof_note = "every input once, x/f/status once (SURVEY.md 8d)"
-    if gw == 0 and not (args.flags & 8):
-        # CTA-per-QP shapes: CI (8*n*m bytes) no longer fits on chip and the algorithm itself reads all of
-        # it in every violated-constraint scan, so that is the algorithmic traffic
-        probe = mgqp_b200.solve_quadprog_batched(*dev_in, flags=args.flags, want_active_set=True)
-        torch.cuda.synchronize()
-        scans = float(probe.iters.double().mean().item()) + 1.0
-        bytes_per_qp = int(bytes_per_qp + (scans - 1.0) * 8 * n * m)
-        roof_note = f"inputs once + CI re-read in each of the {scans:.1f} scans per QP (SURVEY.md 8a a7)"
     achieved = B * bytes_per_qp / (kern_ms / 1e3) / 1e9
-    kname = {1: "gi_lane_kernel<%d> (one QP per lane)" % n, 0: "gi_large_kernel (one QP per CTA)"}.get(
-        gw, "gi_small_kernel<%d> (%d lanes per QP)" % (gw, gw))
+    kname = kernel_name(mgqp_b200, n, p, m)
     if args.flags & 8:
         kname = "gi_small_kernel (lane groups, forced)"
     if args.flags & 16:
@@ -295,60 +526,53 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": f"{name}: {B} QPs per GPU, n={n} p={p} m={m} ({CONFIG_NOTE[name]})",
                    "l2": f"inputs {B * bytes_per_qp / 1e6:.0f} MB per step > 126 MB L2, read once per step",
                    "mode": "fast_math" if args.flags & 1 else "exact (bit-identical to QuadProg++)",
-                   "kernel": f"{kname}, {warps} warps/CTA, {smem} B smem/CTA", "flags": args.flags,
+                   "kernel": kname, "flags": args.flags,
                    "status_counts": np.bincount(status, minlength=5).tolist()},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "matches_device_leg": e2e_same, "host_input_bytes_per_step": int(host_bytes),
+                "transport": "CI column-compressed on the host cores (row, value)" if h2d < 0.8 * host_bytes
+                             else "dense (every field as the caller holds it)",
                 "api": "solve_quadprog_batched_host (C ABI, pinned host buffers, chunked 2-stream pipeline; CI is "
-                       "packed on the host cores into (row, value) columns when every column is a bound"
+                       "packed on the host cores into (row, value) columns when every column is a bound and the "
+                       "rank has the host threads to outrun the link"
                        + (" -- disabled by --flags 32)" if args.flags & 32 else ")")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_qp": bytes_per_qp, "bytes_note": roof_note,
-                     "kernel_ms": kern_ms},
+                     "traffic": None, "peak_source": peak_src, "bytes_per_qp": bytes_per_qp,
+                     "bytes_note": "every input once, x/f/status once (SURVEY.md 8d)", "kernel_ms": kern_ms},
     }
-    if gw == 0 and not (args.flags & 8):
-        # SURVEY.md 8d for the horizon-stacked shape: the dense factorisation part on its own
-        # (Cholesky n^3/3 + triangular inverse n^3/3 + solve 2n^2 flops), timed by solving the same G, g0
-        # with no constraints, against an fp64 GEMM peak measured here with torch.matmul.
-        z = lambda *sh: torch.zeros(sh, dtype=torch.float64, device=dev)
-        bare = [dev_in[0], dev_in[1], z(B, n, 0), z(B, 0), z(B, n, 0), z(B, 0)]
-        mgqp_b200.solve_quadprog_batched(*bare, flags=args.flags | 16)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            mgqp_b200.solve_quadprog_batched(*bare, flags=args.flags | 16)
-        e1.record()
-        torch.cuda.synchronize()
-        dense_ms = e0.elapsed_time(e1) / 3
-        flops = (2.0 * n ** 3 / 3.0 + 2.0 * n * n) * B
-        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-        torch.matmul(a, a)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            torch.matmul(a, a)
-        e1.record()
-        torch.cuda.synchronize()
-        p64 = 3 * 2.0 * 4096 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
-        line["dense_part"] = {"what": "set-up only (Cholesky, J = L^-T, x0): same G, g0, p = m = 0", "ms": dense_ms,
-                              "tflops": flops / (dense_ms / 1e3) / 1e12, "peak_tflops": p64,
-                              "peak_source": "torch.matmul fp64 4096^3 on this GPU",
-                              "frac": flops / (dense_ms / 1e3) / 1e12 / p64,
-                              "note": "plain FP64 FMA units in reference summation order; no DMMA (it would change "
-                                      "the rounding order of the exact mode)"}
     if line_cpu:
         line["cpu_baseline"] = line_cpu
+    if contenders:
+        line["cpu_baseline"]["contenders"] = contenders
     if parity:
         line["parity_check"] = parity
+    if c5s:
+        line["c5_sharded"] = c5s
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
             line["roofline"]["traffic"] = json.load(open(tr)).get(name)
         except Exception:
             pass
+    # ---- every other BASELINE config, outside the timed regions above (N = 1 only)
+    if world == 1 and not args.no_extras and name == "C2":
+        configs = {}
+        for cname, cB, csteps in EXTRA_CONFIGS:
+            try:
+                configs[cname] = extra_config_record(mgqp_b200, cname, cB, csteps, dev, peak)
+            except Exception as e:  # a failing sub-record must not take the headline line with it
+                configs[cname] = {"error": repr(e)}
+        try:
+            configs["C4"] = c4_record(mgqp_b200, dev, peak, C4_FULL)
+        except Exception as e:
+            configs["C4"] = {"error": repr(e)}
+        try:
+            configs["C1_latency"] = c1_latency_record(mgqp_b200)
+        except Exception as e:
+            configs["C1_latency"] = {"error": repr(e)}
+        line["configs"] = configs
     print(json.dumps(line))
 
 
@@ -361,8 +585,10 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(QPS_PER_GPU))  # C2 = the headline config
     ap.add_argument("--batch", type=int, default=0, help="QPs per GPU per step (default: the workload's)")
     ap.add_argument("--flags", type=int, default=0, help="MGQP_FLAG_* bits (1 = fast math)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: --steps)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records (other BASELINE configs, C1 latency, c5_sharded) of the default run")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

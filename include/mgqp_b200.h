@@ -172,6 +172,13 @@ int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int3
 /* Compulsory HBM bytes per QP for a shape (every input once, x/f/status once); SURVEY.md 8(d). */
 int64_t mgqp_algorithmic_bytes(int32_t n, int32_t p, int32_t m);
 
+/* Bench hook (BASELINE.json configs[0], the single-QP-per-cycle path): wall-clock microseconds of `reps`
+ * consecutive calls of the C++ drop-in solve_quadprog() (QuadProg++.hh:69-72) on one QP in QuadProg++ layout.
+ * us_out[reps]; x_out[n] / f_out (optional) receive the last call's answer.  Returns 0, -1 if a call threw. */
+int mgqp_dropin_latency(int32_t n, int32_t p, int32_t m, const double* G, const double* g0, const double* CE,
+                        const double* ce0, const double* CI, const double* ci0, int reps, double* us_out,
+                        double* x_out, double* f_out);
+
 #ifdef __cplusplus
 }
 #endif

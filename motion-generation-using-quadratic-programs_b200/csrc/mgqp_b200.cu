@@ -73,6 +73,15 @@ struct DeviceCtx {
   // pinned host staging for the column-compressed CI of one chunk (values, rows), per buffer set
   void* pack_host[2] = {nullptr, nullptr};
   size_t pack_cap[2] = {0, 0};
+  // the library's own pool for its stream-ordered workspaces (CTA-per-QP kernel, retry pass): the device's
+  // default pool belongs to the host application
+  cudaMemPool_t pool = nullptr;
+  // single-QP path (mgqp_solve_one, the C++ drop-in): one stream, one pinned and one device staging block
+  std::mutex one_mu;
+  cudaStream_t one_st = nullptr;
+  double* one_host = nullptr;
+  double* one_dev = nullptr;
+  size_t one_cap = 0;  // doubles
 };
 DeviceCtx g_dev[kMaxDev];
 
@@ -89,13 +98,18 @@ int device_ctx(int device, DeviceCtx** out) {
     CU(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     {
-      // stream-ordered workspaces (CTA-per-QP kernel, retry pass) are allocated per call: keep what they
-      // free in the device's pool instead of handing it back to the driver at every synchronisation
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
+      // stream-ordered workspaces (CTA-per-QP kernel, retry pass) are allocated per call from a pool of the
+      // library's own: freed blocks stay cached there (up to 1 GB; more goes back to the driver at the next
+      // synchronisation) instead of being parked in the device's default pool, which the application uses
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof props);
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      CU(cudaMemPoolCreate(&c.pool, &props));
+      unsigned long long keep = 1ull << 30;
+      cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     CU(cudaMalloc(&c.tickets, kTicketRing * sizeof(unsigned)));
     CU(cudaMemset(c.tickets, 0, kTicketRing * sizeof(unsigned)));
@@ -282,7 +296,7 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
   if (ctas > cap) ctas = cap;
   if (ctas < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "workspace of %lld bytes per QP is too large", ws_bytes);
   void* ws = nullptr;
-  CU(cudaMallocAsync(&ws, (size_t)(ctas * ws_bytes), st));
+  CU(cudaMallocFromPoolAsync(&ws, (size_t)(ctas * ws_bytes), ctx->pool, st));
   P.workspace = static_cast<double*>(ws);
   kern<<<(unsigned)ctas, lp.T, lp.v.smem_bytes, st>>>(P);
   g_launches.fetch_add(1);
@@ -291,6 +305,13 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
   if (e != cudaSuccess) return fail(MGQP_ERR_CUDA, "gi_large_kernel launch failed: %s", cudaGetErrorString(e));
   return MGQP_OK;
 }
+
+// the caller's current device is put back when an entry point returns
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int validate(const mgqp_batch* d) {
   if (!d) return fail(MGQP_ERR_INVALID_ARG, "null batch descriptor");
@@ -452,9 +473,11 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   if (rc || d->batch == 0) return rc;
   if (d->n > 1024) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "MGQP_FLAG_RETRY_WITHOUT_CI serves n <= 1024");
   const long long B = d->batch, n = d->n, p = d->p, m = d->m;
+  DeviceCtx* rctx = nullptr;
+  if ((rc = device_ctx(device, &rctx))) return rc;
   AsyncBuf idx_buf, ws_buf;
   idx_buf.st = ws_buf.st = st;
-  CU(cudaMallocAsync(&idx_buf.p, (size_t)B * 8 + 8, st));
+  CU(cudaMallocFromPoolAsync(&idx_buf.p, (size_t)B * 8 + 8, rctx->pool, st));
   long long* idx = static_cast<long long*>(idx_buf.p);
   unsigned long long* count = reinterpret_cast<unsigned long long*>(idx + B);
   CU(cudaMemsetAsync(count, 0, 8, st));
@@ -475,7 +498,7 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   const long long c = (long long)cnt;
   const size_t dbl = (size_t)c * (n * n + n + n * p + p + n + 1);
   const size_t ints = (size_t)c * (3 + p);
-  CU(cudaMallocAsync(&ws_buf.p, dbl * 8 + ints * 4 + 64, st));
+  CU(cudaMallocFromPoolAsync(&ws_buf.p, dbl * 8 + ints * 4 + 64, rctx->pool, st));
   double* G2 = static_cast<double*>(ws_buf.p);
   double* g02 = G2 + c * n * n;
   double* CE2 = g02 + c * n;
@@ -603,7 +626,7 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
       CU(cudaMemcpyAsync(f.dst, f.src, (size_t)f.size * 8, cudaMemcpyHostToDevice, st));
       *f.dstride = 0;
       g_h2d_bytes += f.size * 8;
-    } else if (k < 2 && pack && cnt > 1 && mgqp_blocks_all_equal(f.src + q0 * f.stride, f.stride, f.size, cnt, 0)) {
+    } else if (k < 2 && cnt > 1 && mgqp_blocks_all_equal(f.src + q0 * f.stride, f.stride, f.size, cnt, 0)) {
       // G / g0 identical in every QP of the chunk (the reference's caller: G = I, g0 = 0): one instance
       CU(cudaMemcpyAsync(f.dst, f.src + q0 * f.stride, (size_t)f.size * 8, cudaMemcpyHostToDevice, st));
       *f.dstride = 0;
@@ -647,7 +670,7 @@ long long default_chunk(const mgqp_batch* h) {
 }
 
 // Pull chunks from `next` until the batch is exhausted; two streams, two buffer sets.
-int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long>* next) {
+int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long>* next, int ndev = 1) {
   int rc = validate(h);
   if (rc) return rc;
   DeviceCtx* ctx = nullptr;
@@ -681,7 +704,9 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     const double rest = 8.0 * (n * n + n + n * p + p + m) + 8.0 * (n + 1) + 4.0;
     const double link = 50e9, per_thread = 6e9;
     const double t_dense = (rest + 8.0 * n * m) / link;
-    const double t_link = (rest + 9.0 * m) / link, t_cpu = 8.0 * n * m / (per_thread * mgqp_host_pack_threads());
+    // (the devices of a multi-device call share the host's packing threads)
+    const double threads = (double)mgqp_host_pack_threads() / (ndev > 0 ? ndev : 1);
+    const double t_link = (rest + 9.0 * m) / link, t_cpu = 8.0 * n * m / (per_thread * (threads < 1.0 ? 1.0 : threads));
     pack = (t_link > t_cpu ? t_link : t_cpu) < 0.8 * t_dense;
   }
   if (pack) {
@@ -723,6 +748,7 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
 extern "C" {
 
 int solve_quadprog_batched(const mgqp_batch* d, int device, void* stream) {
+  DeviceGuard guard;
   return solve_device(d, device, static_cast<cudaStream_t>(stream));
 }
 
@@ -732,6 +758,7 @@ int solve_quadprog_batched_host(const mgqp_batch* h, int device, int64_t chunk) 
   if (rc) return rc;
   if (chunk <= 0) chunk = default_chunk(h);
   std::atomic<long long> next(0);
+  DeviceGuard guard;
   return pump(h, device, chunk, &next);
 }
 
@@ -752,7 +779,7 @@ int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int nd
   for (int i = 0; i < ndev; i++)
     th.emplace_back([&, i]() {
       g_h2d_bytes = g_d2h_bytes = 0;
-      rcs[i] = pump(h, devices[i], chunk, &next);
+      rcs[i] = pump(h, devices[i], chunk, &next, ndev);
       if (rcs[i]) errs[i] = g_last_error;
       up += g_h2d_bytes;
       down += g_d2h_bytes;
@@ -768,18 +795,53 @@ int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int nd
 int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const double* g0, const double* CE,
                    const double* ce0, const double* CI, const double* ci0, double* x, double* f, int32_t* status,
                    double* G_factor, int device) {
-  mgqp_batch h;
-  memset(&h, 0, sizeof h);
-  h.n = n; h.p = p; h.m = m; h.batch = 1;
-  h.G = G; h.g0 = g0; h.CE = CE; h.ce0 = ce0; h.CI = CI; h.ci0 = ci0;
-  h.sG = (int64_t)n * n; h.sg0 = n; h.sCE = (int64_t)n * p; h.sce0 = p; h.sCI = (int64_t)n * m; h.sci0 = m;
-  h.x = x; h.f = f; h.status = status;
-  // empty blocks may come in as null pointers (Matrix(n,0)); give validate() something to look at
-  static const double dummy = 0.0;
-  if (p == 0) { h.CE = &dummy; h.ce0 = &dummy; }
-  if (m == 0) { h.CI = &dummy; h.ci0 = &dummy; }
-  int rc = solve_quadprog_batched_host(&h, device, 1);
+  // One stream, one pinned and one device staging block per device, kept across calls: a call is one H2D
+  // copy, one kernel launch (static schedule: no work-queue memset), one D2H copy and one synchronisation.
+  if (n < 1 || p < 0 || m < 0 || !G || !g0 || !x || !f || !status || (p && (!CE || !ce0)) || (m && (!CI || !ci0)))
+    return fail(MGQP_ERR_INVALID_ARG, "mgqp_solve_one: bad argument");
+  DeviceCtx* ctx = nullptr;
+  int rc = device_ctx(device, &ctx);
   if (rc) return rc;
+  DeviceGuard guard;
+  CU(cudaSetDevice(device));
+  const size_t sz[6] = {(size_t)n * n, (size_t)n, (size_t)n * p, (size_t)p, (size_t)n * m, (size_t)m};
+  const double* src[6] = {G, g0, CE, ce0, CI, ci0};
+  size_t off[7];
+  off[0] = 0;
+  for (int k = 0; k < 6; k++) off[k + 1] = off[k] + ((sz[k] + 1) & ~(size_t)1);  // 16-byte aligned fields
+  const size_t in_dbl = off[6], out_dbl = (size_t)n + 2;                          // x | f | status
+  std::lock_guard<std::mutex> lk(ctx->one_mu);
+  if (!ctx->one_st) CU(cudaStreamCreateWithFlags(&ctx->one_st, cudaStreamNonBlocking));
+  if (ctx->one_cap < in_dbl + out_dbl) {
+    if (ctx->one_host) cudaFreeHost(ctx->one_host);
+    if (ctx->one_dev) cudaFree(ctx->one_dev);
+    ctx->one_host = nullptr; ctx->one_dev = nullptr; ctx->one_cap = 0;
+    const size_t cap = (in_dbl + out_dbl) * 2 + 64;
+    CU(cudaHostAlloc((void**)&ctx->one_host, cap * 8, cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&ctx->one_dev, cap * 8));
+    ctx->one_cap = cap;
+  }
+  double* hb = ctx->one_host;
+  double* db = ctx->one_dev;
+  for (int k = 0; k < 6; k++)
+    if (sz[k]) memcpy(hb + off[k], src[k], sz[k] * 8);
+  cudaStream_t st = ctx->one_st;
+  CU(cudaMemcpyAsync(db, hb, in_dbl * 8, cudaMemcpyHostToDevice, st));
+  mgqp_batch d;
+  memset(&d, 0, sizeof d);
+  d.n = n; d.p = p; d.m = m; d.batch = 1;
+  d.G = db + off[0]; d.g0 = db + off[1]; d.CE = db + off[2]; d.ce0 = db + off[3]; d.CI = db + off[4]; d.ci0 = db + off[5];
+  d.sG = (int64_t)sz[0]; d.sg0 = n; d.sCE = (int64_t)sz[2]; d.sce0 = p; d.sCI = (int64_t)sz[4]; d.sci0 = m;
+  d.x = db + in_dbl; d.f = db + in_dbl + n; d.status = reinterpret_cast<int32_t*>(db + in_dbl + n + 1);
+  d.flags = MGQP_FLAG_STATIC_SCHEDULE;
+  if ((rc = solve_device(&d, device, st))) return rc;
+  CU(cudaMemcpyAsync(hb + in_dbl, db + in_dbl, out_dbl * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(x, hb + in_dbl, (size_t)n * 8);
+  *f = hb[in_dbl + n];
+  memcpy(status, hb + in_dbl + n + 1, 4);
+  g_h2d_bytes = (long long)in_dbl * 8;
+  g_d2h_bytes = (long long)out_dbl * 8;
   if (G_factor) {
     // The reference leaves chol(G) in G (lower factor mirrored into the upper triangle,
     // QuadProg++.hh:42-45).  n is tiny on this path; the factor is recomputed on the host in the

@@ -10,6 +10,8 @@ Shapes:
   C3  n=14, p=7,  m=60    task-space QP with slacks
   C4  n=350,p=0,  m=2100  horizon-stacked MPC QP (7 DoF x 50 steps)
   C5  C2 shape, ~10 % made infeasible by a contradictory bound pair
+  C5D C5 with a second equality (p=2): ~4 % of the QPs carry a duplicated equality column (about a quarter of them end up below the
+      solver's dependence threshold: ~1 % status 3, the reference's runtime_error "Constraints are linearly dependent")
   S0  n=14, p=10, m=28    as-shipped level 0 (src/mgqp.cpp:1076-1143: G=I, g0=0, CI=[-I;+I])
   S2  n=14, p=1,  m=28    as-shipped level 2
 
@@ -27,10 +29,11 @@ SHAPES = {
     "C3": (14, 7, 60),
     "C4": (350, 0, 2100),
     "C5": (7, 1, 42),
+    "C5D": (7, 2, 42),
     "S0": (14, 10, 28),
     "S2": (14, 1, 28),
 }
-_CONFIG_ID = {"S0": 1, "S2": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5}
+_CONFIG_ID = {"S0": 1, "S2": 1, "C2": 2, "C3": 3, "C4": 4, "C5": 5, "C5D": 6}
 
 
 @dataclass
@@ -104,6 +107,56 @@ def make_c5(B: int, seed: int | None = None) -> QPBatch:
     return make_c2(B, seed, infeasible_frac=0.10, name="C5")
 
 
+def make_c5d(B: int, seed: int | None = None, dependent_frac: float = 0.04) -> QPBatch:
+    """SURVEY.md 8(d) C5: ~10 % infeasible and ~1 % answered "linearly dependent" (duplicated equality columns, p = 2;
+    an exactly duplicated column falls below the solver's eps * R_norm threshold only about one time in four)."""
+    b = make_c2(B, 1234 + _CONFIG_ID["C5D"] if seed is None else seed, infeasible_frac=0.10, name="C5")
+    rng = np.random.default_rng((1234 + 77 * _CONFIG_ID["C5D"]) if seed is None else seed + 77)
+    CE = np.concatenate([b.CE, rng.standard_normal((B, b.n, 1))], axis=2)
+    ce0 = np.concatenate([b.ce0, 0.3 * rng.standard_normal((B, 1))], axis=1)
+    dup = rng.random(B) < dependent_frac
+    CE[dup, :, 1] = CE[dup, :, 0]
+    return QPBatch("C5D", b.n, 2, b.m, b.G, b.g0, CE, ce0, b.CI, b.ci0)
+
+
+def make_c4_device(B: int, device, seed: int = 1234 + 4, dof: int = 7, steps: int = 50):
+    """The C4 workload generated ON THE DEVICE (torch tensors in field order): at BASELINE.json's 10k QPs the
+    batch is 69 GB, which no host generator fills in reasonable time.  Same construction as make_c4 (dense SPD
+    G = H'H/n + I, integrator-matrix bounds with per-QP limits), torch's generator instead of numpy's."""
+    import torch
+    n = dof * steps
+    m = 6 * n
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    G = torch.empty((B, n, n), dtype=torch.float64, device=device)
+    eye = torch.eye(n, dtype=torch.float64, device=device)
+    for lo in range(0, B, 256):  # chunked: the n*n temporaries stay small
+        hi = min(B, lo + 256)
+        H = torch.randn((hi - lo, n, n), dtype=torch.float64, device=device, generator=gen)
+        G[lo:hi] = torch.einsum("bki,bkj->bij", H, H) / n + eye
+    g0 = 2.0 * torch.randn((B, n), dtype=torch.float64, device=device, generator=gen)
+    rows = torch.from_numpy(_c4_constraint_rows(dof, steps)).to(device)            # [m, n], row = constraint
+    CI = rows.t().contiguous()[None].expand(B, n, m).contiguous()
+    lim = torch.cat([torch.full((2 * n,), 1.0), torch.full((2 * n,), 0.5), torch.full((2 * n,), 0.3)]).to(device).double()
+    ci0 = lim[None, :] * (0.5 + torch.rand((B, m), dtype=torch.float64, device=device, generator=gen))
+    CE = torch.zeros((B, n, 0), dtype=torch.float64, device=device)
+    ce0 = torch.zeros((B, 0), dtype=torch.float64, device=device)
+    return [G, g0, CE, ce0, CI, ci0]
+
+
+def _c4_constraint_rows(dof: int, steps: int) -> np.ndarray:
+    n = dof * steps
+    dt = 0.05
+    I = np.eye(dof)
+    S = np.zeros((n, n))  # vel_k = sum_{j<=k} dt a_j
+    P = np.zeros((n, n))  # pos_k = sum_{j<=k} (k-j+0.5) dt^2 a_j
+    for k in range(steps):
+        for j in range(k + 1):
+            S[k * dof:(k + 1) * dof, j * dof:(j + 1) * dof] = dt * I
+            P[k * dof:(k + 1) * dof, j * dof:(j + 1) * dof] = (k - j + 0.5) * dt * dt * I
+    return np.concatenate([np.eye(n), -np.eye(n), S, -S, P, -P], axis=0)
+
+
 def make_c3(B: int, seed: int | None = None) -> QPBatch:
     n, p, m = SHAPES["C3"]
     rng = np.random.default_rng(1234 + _CONFIG_ID["C3"] if seed is None else seed)
@@ -143,15 +196,7 @@ def make_c4(B: int, seed: int | None = None, dof: int = 7, steps: int = 50) -> Q
     rng = np.random.default_rng(1234 + _CONFIG_ID["C4"] if seed is None else seed)
     G = _spd(rng, B, n)
     g0 = 2.0 * rng.standard_normal((B, n))
-    dt = 0.05
-    I = np.eye(dof)
-    S = np.zeros((n, n))  # vel_k = sum_{j<=k} dt a_j
-    P = np.zeros((n, n))  # pos_k = sum_{j<=k} (k-j+0.5) dt^2 a_j
-    for k in range(steps):
-        for j in range(k + 1):
-            S[k * dof:(k + 1) * dof, j * dof:(j + 1) * dof] = dt * I
-            P[k * dof:(k + 1) * dof, j * dof:(j + 1) * dof] = (k - j + 0.5) * dt * dt * I
-    rows = np.concatenate([np.eye(n), -np.eye(n), S, -S, P, -P], axis=0)  # [m, n], row = constraint
+    rows = _c4_constraint_rows(dof, steps)  # [m, n], row = constraint
     CI = np.broadcast_to(rows.T[None], (B, n, m)).copy()
     lim = np.concatenate([np.full(2 * n, 1.0), np.full(2 * n, 0.5), np.full(2 * n, 0.3)])
     ci0 = lim[None, :] * rng.uniform(0.5, 1.5, (B, m))
@@ -220,6 +265,8 @@ def make(name: str, B: int, seed: int | None = None) -> QPBatch:
         return make_c4(B, seed)
     if name == "C5":
         return make_c5(B, seed)
+    if name == "C5D":
+        return make_c5d(B, seed)
     if name == "S0":
         return make_shipped(B, 0, seed)
     if name == "S2":

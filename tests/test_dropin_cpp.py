@@ -1,7 +1,8 @@
 """The C++ drop-in: a translation unit written exactly like the reference's caller
 (src/mgqp.cpp:695-708: resize / operator[] fill / t(CE) / solve_quadprog) must compile against
-include/QuadProgpp/QuadProg++.hh and link against libmgqp_b200.so.  Compile + link run on CPU;
-executing it needs a GPU."""
+include/QuadProgpp/QuadProg++.hh and link against libmgqp_b200.so -- and so must the same file compiled
+against the REFERENCE's own headers (object-layout compatibility of Matrix / Vector: built by oracle/Makefile
+into oracle/_ref/ where /root/reference exists).  Compile + link run on CPU; executing needs a GPU."""
 import os
 import subprocess
 
@@ -10,32 +11,8 @@ import pytest
 
 from conftest import ROOT
 
-SRC = r'''
-#include <cstdio>
-#include <stdexcept>
-#include <cmath>
-#include "QuadProg++.hh"
-int main() {
-  // K1 of SURVEY.md 8c, assembled the way solveNextStep does: rows = constraints, then t()
-  ArrayHH::Matrix<double> G, CE, CI; ArrayHH::Vector<double> g0, ce0, ci0, x;
-  G.resize(2, 2); G[0][0] = 4; G[0][1] = -2; G[1][0] = -2; G[1][1] = 4;
-  g0.resize(2); g0[0] = 6; g0[1] = 0;
-  CE.resize(1, 2); CE[0][0] = 1; CE[0][1] = 1; ce0.resize(1); ce0[0] = -3;
-  CI.resize(3, 2); CI[0][0] = 1; CI[0][1] = 0; CI[1][0] = 0; CI[1][1] = 1; CI[2][0] = 1; CI[2][1] = 1;
-  ci0.resize(3); ci0[0] = 0; ci0[1] = 0; ci0[2] = -2;
-  x.resize(2);
-  double f = solve_quadprog(G, g0, ArrayHH::t(CE), ce0, ArrayHH::t(CI), ci0, x);
-  std::printf("f=%.17g x=%.17g %.17g G00=%.17g\n", f, x[0], x[1], G[0][0]);
-  // retry path of src/mgqp.cpp:723-725: inequalities dropped
-  CI.resize(0, 2); ci0.resize(0);
-  ArrayHH::Matrix<double> G2; G2.resize(2, 2); G2[0][0] = 4; G2[0][1] = -2; G2[1][0] = -2; G2[1][1] = 4;
-  f = solve_quadprog(G2, g0, ArrayHH::t(CE), ce0, ArrayHH::t(CI), ci0, x);
-  std::printf("f2=%.17g\n", f);
-  try { ArrayHH::Matrix<double> B; B.resize(3, 1); solve_quadprog(G2, g0, B, ce0, ArrayHH::t(CI), ci0, x); }
-  catch (const std::logic_error& e) { std::printf("logic_error: %s\n", e.what()); }
-  return 0;
-}
-'''
+SRC_FILE = os.path.join(ROOT, "tests", "dropin_caller.cc")
+REFHDR_EXE = os.path.join(ROOT, "oracle", "_ref", "dropin_caller_refhdr")
 
 
 @pytest.fixture(scope="module")
@@ -43,8 +20,7 @@ def exe(tmp_path_factory):
     import __graft_entry__ as g
     g.build()
     d = tmp_path_factory.mktemp("dropin")
-    src = d / "caller.cc"
-    src.write_text(SRC)
+    src = SRC_FILE
     out = d / "caller"
     pkg = os.path.join(ROOT, "motion-generation-using-quadratic-programs_b200")
     subprocess.check_call(["g++", "-std=gnu++14", "-O1", "-I", os.path.join(ROOT, "include", "QuadProgpp"), str(src),
@@ -58,7 +34,10 @@ def test_reference_style_caller_compiles_and_links(exe):
 
 @pytest.mark.gpu
 def test_reference_style_caller_runs(exe):
-    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    _check_output(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+
+
+def _check_output(out):
     z = np.load(os.path.join(ROOT, "tests", "golden", "kat_K1_demo.npz"))
     line = out.splitlines()[0]
     f = float(line.split("f=")[1].split()[0])
@@ -66,3 +45,22 @@ def test_reference_style_caller_runs(exe):
     assert f == float(z["f"]) and xs == list(z["x"])
     assert "G00=2" in line                      # G overwritten by its Cholesky factor
     assert "logic_error: The matrix CE is incompatible (incorrect number of rows 3 , expecting 2)" in out
+
+
+def test_caller_compiled_against_reference_headers_links():
+    """Where the reference tree is present the same caller is built against ITS headers (oracle/Makefile)."""
+    if not os.path.isdir("/root/reference/include/QuadProgpp"):
+        pytest.skip("reference tree absent (GPU box): the binary was built where it exists")
+    import __graft_entry__ as g
+    g.build()
+    assert os.path.exists(REFHDR_EXE), "oracle/Makefile did not build oracle/_ref/dropin_caller_refhdr"
+    syms = subprocess.run(["nm", "-D", "--undefined-only", REFHDR_EXE], capture_output=True, text=True).stdout
+    assert "_Z14solve_quadprogRN7ArrayHH6MatrixIdEERNS_6VectorIdEERKS1_RKS4_S7_S9_S5_" in syms
+
+
+@pytest.mark.gpu
+def test_caller_compiled_against_reference_headers_runs():
+    """Matrix / Vector objects laid out by the REFERENCE's Array.hh, solved by libmgqp_b200.so."""
+    if not os.path.exists(REFHDR_EXE):
+        pytest.skip("oracle/_ref/dropin_caller_refhdr was not built (needs /root/reference at build time)")
+    _check_output(subprocess.run([REFHDR_EXE], capture_output=True, text=True, check=True).stdout)

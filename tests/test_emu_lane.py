@@ -49,7 +49,7 @@ def _oracle(restatement, b, max_iter=0):
     return restatement.solve_batch(b.n, b.p, b.m, *b.fields(), max_iter=max_iter or default_max_iter(b.p, b.m), threads=4)
 
 
-@pytest.mark.parametrize("name,B", [("C2", 3000), ("C5", 3000)])
+@pytest.mark.parametrize("name,B", [("C2", 3000), ("C5", 3000), ("C5D", 3000)])
 def test_headline_shapes(emu_lib, restatement, name, B):
     b = workloads.make(name, B)
     assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), name)

@@ -45,7 +45,7 @@ def _oracle(restatement, b, max_iter=0):
     return restatement.solve_batch(b.n, b.p, b.m, *b.fields(), max_iter=max_iter or default_max_iter(b.p, b.m), threads=8)
 
 
-@pytest.mark.parametrize("name,B", [("C2", 20001), ("C5", 20003), ("C3", 6001), ("S0", 6001), ("S2", 6001)])
+@pytest.mark.parametrize("name,B", [("C2", 20001), ("C5", 20003), ("C5D", 20005), ("C3", 6001), ("S0", 6001), ("S2", 6001)])
 def test_benchmark_shapes_bit_identical(gpu, restatement, name, B):
     b = workloads.make(name, B)
     assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), name)

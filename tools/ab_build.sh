@@ -8,7 +8,7 @@ mkdir -p variants
 CS=motion-generation-using-quadratic-programs_b200/csrc
 for spec in "$@"; do
   name=${spec%%=*}; flags=${spec#*=}
-  ( nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -shared \
+  ( nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -ffp-contract=off -Xcompiler -fPIC -shared \
       $flags -I include -o variants/$name.so $CS/mgqp_b200.cu $CS/quadprog_dropin.cc $CS/host_pack.cc -Xptxas -v 2>&1 \
       | grep -A2 "Compiling.*gi_lane_kernelILi7ELb0" | tail -1 | sed "s/^/$name: /" ) &
 done
