@@ -172,6 +172,38 @@ int mgqp_plan(int32_t n, int32_t p, int32_t m, int32_t* smem_bytes_per_cta, int3
 /* Compulsory HBM bytes per QP for a shape (every input once, x/f/status once); SURVEY.md 8(d). */
 int64_t mgqp_algorithmic_bytes(int32_t n, int32_t p, int32_t m);
 
+/* ---- The solver's two callers, batched, for the 7-DoF wiring the reference ships
+ * (ops/mgqp.ops:233-240, :256, :289-292): per scenario the QP assembly of updateHook (src/mgqp.cpp:886-1143) and the
+ * priority cascade of solveNextHierarchy (:751-869) -- level 0 = translational task of link 7 + dynamics [M -I] under
+ * the box limits [-I; +I] with log-barrier shaped acceleration limits, level 2 = joint-1 position task in level 0's
+ * null space -- each level solved by the engine above with solveNextStep's infeasible-retry policy (:717-735).
+ * Inputs are the ~0.5 KB of robot state the reference reads from its ports (float32, SoA, [batch][...] row-major),
+ * outputs the 14-vector [qdd; tau] solveNextHierarchy returns and the torque command tau + h (:1152). */
+typedef struct mgqp_scenarios {
+  int64_t batch;
+  const float *q, *qd;           /* [batch][7]   joint angles / velocities (in_robotstatus)          */
+  const float* M;                /* [batch][7][7] joint-space inertia (in_inertia)                    */
+  const float* h;                /* [batch][7]   Coriolis + gravity (in_h)                            */
+  const float *J, *Jd;           /* [batch][3][7] translation Jacobian of link 7 and its derivative   */
+  const float *pos_des, *pos_cur, *vel_des, *vel_cur, *acc_des, *acc_cur; /* [batch][3] task-space targets / state */
+  const float* q1_des;           /* [batch]      desired position of the joint-space task's joint     */
+  float kp_task, kd_task, kp_joint, kd_joint;          /* gains (src/mgqp.cpp:104-110)                 */
+  float acc_p[7], acc_n[7], tau_p[7], tau_n[7], q_sup[7], q_inf[7]; /* limits (ops/mgqp.ops:187-189)  */
+  int32_t joint_task;            /* 0-based joint of the level-2 task (shipped: 0)                    */
+  float* tracking;               /* [batch][14]  [qdd; tau] (zeros where level 0 failed)              */
+  float* torques;                /* [batch][7]   tau + h                                              */
+  int32_t *status0, *status2;    /* [batch] verdicts of the two levels as MGQP_FLAG_RETRY_WITHOUT_CI reports them
+                                    (status2 = -1 where level 0 failed); optional                       */
+  /* optional taps for tests: the level-0 QP as assembled (fp64, solver layout) and the projector */
+  double *tap_CE0, *tap_ce0, *tap_ci0; /* [batch][14][10], [batch][10], [batch][28] */
+  float* tap_Z;                        /* [batch][14][14] */
+} mgqp_scenarios;
+
+/* Device pointers; asynchronous on `stream`. */
+int mgqp_cascade_batched(const mgqp_scenarios* s, int device, void* stream);
+/* Host pointers: state uploaded / answers downloaded chunk by chunk over two streams. */
+int mgqp_cascade_batched_host(const mgqp_scenarios* s, int device, int64_t chunk);
+
 /* Bench hook (BASELINE.json configs[0], the single-QP-per-cycle path): wall-clock microseconds of `reps`
  * consecutive calls of the C++ drop-in solve_quadprog() (QuadProg++.hh:69-72) on one QP in QuadProg++ layout.
  * us_out[reps]; x_out[n] / f_out (optional) receive the last call's answer.  Returns 0, -1 if a call threw. */

@@ -29,6 +29,7 @@ __all__ = [
     "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
     "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL",
     "FLAG_NO_HOST_PACK", "FLAG_RETRY_WITHOUT_CI", "STATUS_RETRIED", "mgqp_batch", "pack_bound_columns", "last_transfer_bytes",
+    "mgqp_scenarios", "CascadeResult", "solve_cascade_batched", "solve_cascade_batched_host",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,6 +60,28 @@ class mgqp_batch(C.Structure):
         ("max_iter", C.c_int32), ("flags", C.c_int32),
         ("CI_val", C.c_void_p), ("CI_row", C.c_void_p), ("sCIv", C.c_int64), ("sCIr", C.c_int64),
     ]
+
+
+class mgqp_scenarios(C.Structure):
+    _fields_ = ([("batch", C.c_int64)]
+                + [(k, C.c_void_p) for k in ("q", "qd", "M", "h", "J", "Jd", "pos_des", "pos_cur", "vel_des", "vel_cur",
+                                             "acc_des", "acc_cur", "q1_des")]
+                + [(k, C.c_float) for k in ("kp_task", "kd_task", "kp_joint", "kd_joint")]
+                + [(k, C.c_float * 7) for k in ("acc_p", "acc_n", "tau_p", "tau_n", "q_sup", "q_inf")]
+                + [("joint_task", C.c_int32)]
+                + [(k, C.c_void_p) for k in ("tracking", "torques", "status0", "status2", "tap_CE0", "tap_ce0",
+                                             "tap_ci0", "tap_Z")])
+
+
+class CascadeResult(NamedTuple):
+    tracking: object       # [B,14] float32: [qdd; tau] as solveNextHierarchy returns it
+    torques: object        # [B,7]  float32: tau + h (src/mgqp.cpp:1152)
+    status0: object
+    status2: object
+    CE0: object = None     # taps (device path, taps=True): the level-0 QP as assembled, the projector
+    ce0: object = None
+    ci0: object = None
+    Z: object = None
 
 
 class QPResult(NamedTuple):
@@ -109,6 +132,10 @@ def lib():
         L.mgqp_pack_bound_columns.restype = C.c_int
         L.mgqp_pack_bound_columns.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                               C.c_void_p, C.c_int64, C.c_int]
+        L.mgqp_cascade_batched.restype = C.c_int
+        L.mgqp_cascade_batched.argtypes = [C.POINTER(mgqp_scenarios), C.c_int, C.c_void_p]
+        L.mgqp_cascade_batched_host.restype = C.c_int
+        L.mgqp_cascade_batched_host.argtypes = [C.POINTER(mgqp_scenarios), C.c_int, C.c_int64]
         L.mgqp_last_transfer_bytes.restype = None
         L.mgqp_last_transfer_bytes.argtypes = [C.POINTER(C.c_int64)] * 2
         _lib = L
@@ -311,6 +338,87 @@ def solve_quadprog_batched_multi(G, g0, CE, ce0, CI, ci0, *, devices, want_activ
     devs = (C.c_int * len(devices))(*devices)
     _check(lib().solve_quadprog_batched_multi(C.byref(d), devs, len(devices), chunk))
     return outs
+
+
+# ------------------------------------------------------------------ the solver's callers, batched
+_SCEN_SHAPES = {"q": (7,), "qd": (7,), "M": (7, 7), "h": (7,), "J": (3, 7), "Jd": (3, 7), "pos_des": (3,), "pos_cur": (3,),
+                "vel_des": (3,), "vel_cur": (3,), "acc_des": (3,), "acc_cur": (3,), "q1_des": ()}
+
+
+def _scenario_desc(state, config, B):
+    from .workloads import SHIPPED_CONFIG
+    cfg = SHIPPED_CONFIG if config is None else config
+    d = mgqp_scenarios()
+    d.batch = B
+    for k in ("kp_task", "kd_task", "kp_joint", "kd_joint"):
+        setattr(d, k, float(cfg[k]))
+    for k in ("acc_p", "acc_n", "tau_p", "tau_n", "q_sup", "q_inf"):
+        v = np.asarray(cfg[k], dtype=np.float32).reshape(-1)
+        if v.size != 7:
+            raise ValueError(f"config[{k!r}] must have 7 entries")
+        setattr(d, k, (C.c_float * 7)(*[float(x) for x in v]))
+    d.joint_task = int(cfg["joint_task"])
+    return d
+
+
+def solve_cascade_batched(state, config=None, *, taps: bool = False, stream=None) -> CascadeResult:
+    """QP assembly (updateHook, src/mgqp.cpp:886-1143) + priority cascade (solveNextHierarchy, :751-869) for a batch
+    of robot states held in CUDA float32 tensors: ``state`` maps the field names of ``mgqp_scenarios`` (q, qd, M, h, J,
+    Jd, pos_des, pos_cur, vel_des, vel_cur, acc_des, acc_cur, q1_des) to ``[B, ...]`` tensors; ``config`` holds the
+    gains and limits (default: as shipped).  Asynchronous on ``stream`` (default: torch's current stream)."""
+    import torch
+
+    q = state["q"]
+    if not q.is_cuda:
+        raise ValueError("solve_cascade_batched takes CUDA tensors; use solve_cascade_batched_host for host arrays")
+    dev, B = q.device, q.shape[0]
+    d = _scenario_desc(state, config, B)
+    keep = []
+    for k, shp in _SCEN_SHAPES.items():
+        t = state[k]
+        if t.dtype != torch.float32 or tuple(t.shape) != (B,) + shp or not t.is_contiguous() or t.device != dev:
+            raise ValueError(f"state[{k!r}] must be a contiguous float32 CUDA tensor of shape {(B,) + shp}")
+        setattr(d, k, t.data_ptr())
+        keep.append(t)
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = CascadeResult(torch.empty((B, 14), **f32), torch.empty((B, 7), **f32),
+                        torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+                        *((torch.empty((B, 14, 10), dtype=torch.float64, device=dev),
+                           torch.empty((B, 10), dtype=torch.float64, device=dev),
+                           torch.empty((B, 28), dtype=torch.float64, device=dev),
+                           torch.empty((B, 14, 14), **f32)) if taps else ()))
+    d.tracking, d.torques = out.tracking.data_ptr(), out.torques.data_ptr()
+    d.status0, d.status2 = out.status0.data_ptr(), out.status2.data_ptr()
+    if taps:
+        d.tap_CE0, d.tap_ce0, d.tap_ci0, d.tap_Z = (out.CE0.data_ptr(), out.ce0.data_ptr(), out.ci0.data_ptr(),
+                                                    out.Z.data_ptr())
+    if B == 0:
+        return out
+    if stream is None:
+        stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+    _check(lib().mgqp_cascade_batched(C.byref(d), dev.index if dev.index is not None else 0, C.c_void_p(sptr)))
+    return out
+
+
+def solve_cascade_batched_host(state, config=None, *, device: int = 0, chunk: int = 0,
+                               out: Optional[CascadeResult] = None) -> CascadeResult:
+    """Host (numpy float32) arrays in, numpy arrays out: ~0.5 KB of robot state up and 84 bytes of command down per
+    scenario, the QPs themselves are assembled, solved and projected on the device."""
+    arrs = {k: np.ascontiguousarray(state[k], dtype=np.float32) for k in _SCEN_SHAPES}
+    B = arrs["q"].shape[0]
+    d = _scenario_desc(state, config, B)
+    for k, shp in _SCEN_SHAPES.items():
+        if arrs[k].shape != (B,) + shp:
+            raise ValueError(f"state[{k!r}] must have shape {(B,) + shp}, got {arrs[k].shape}")
+        setattr(d, k, arrs[k].ctypes.data)
+    if out is None:
+        out = CascadeResult(np.empty((B, 14), np.float32), np.empty((B, 7), np.float32), np.empty(B, np.int32),
+                            np.empty(B, np.int32))
+    d.tracking, d.torques = out.tracking.ctypes.data, out.torques.ctypes.data
+    d.status0, d.status2 = out.status0.ctypes.data, out.status2.ctypes.data
+    _check(lib().mgqp_cascade_batched_host(C.byref(d), device, chunk))
+    return out
 
 
 # ------------------------------------------------------------------ the reference's own call

@@ -23,6 +23,7 @@
 #include "gi_large_kernel.cuh"
 #include "gi_small_kernel.cuh"
 #include "retry.cuh"
+#include "cascade.cuh"
 
 namespace {
 
@@ -82,6 +83,11 @@ struct DeviceCtx {
   double* one_host = nullptr;
   double* one_dev = nullptr;
   size_t one_cap = 0;  // doubles
+  // cascade: G = I14, g0 = 0 and limitsMatrix = [-I; +I] in column-compressed form, one instance for every scenario
+  double* casc_const = nullptr;
+  cudaStream_t casc_st[2] = {nullptr, nullptr};
+  void* casc_arena[2] = {nullptr, nullptr};
+  size_t casc_cap[2] = {0, 0};
 };
 DeviceCtx g_dev[kMaxDev];
 
@@ -742,6 +748,186 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
   return rc;
 }
 
+// ------------------------------------------------------------------ the solver's callers, batched
+int cascade_device(const mgqp_scenarios* s, int device, cudaStream_t st) {
+  if (!s) return fail(MGQP_ERR_INVALID_ARG, "null scenario descriptor");
+  if (s->batch < 0) return fail(MGQP_ERR_INVALID_ARG, "batch = %lld must be >= 0", (long long)s->batch);
+  if (!s->q || !s->qd || !s->M || !s->h || !s->J || !s->Jd || !s->pos_des || !s->pos_cur || !s->vel_des ||
+      !s->vel_cur || !s->acc_des || !s->acc_cur || !s->q1_des || !s->tracking || !s->torques)
+    return fail(MGQP_ERR_INVALID_ARG, "null scenario field");
+  if (s->joint_task < 0 || s->joint_task >= kDof) return fail(MGQP_ERR_INVALID_ARG, "joint_task out of range");
+  if (s->batch == 0) return MGQP_OK;
+  DeviceCtx* ctx = nullptr;
+  int rc = device_ctx(device, &ctx);
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->casc_const) {
+      // [G = I14 (196) | g0 = 0 (14) | CI_val (28) | CI_row (28 bytes, padded)]
+      std::vector<double> hc(196 + 14 + 28 + 4, 0.0);
+      for (int i = 0; i < kN; i++) hc[i * kN + i] = 1.0;
+      for (int c = 0; c < kN; c++) { hc[210 + c] = -1.0; hc[210 + kN + c] = 1.0; }   // src/mgqp.cpp:1111-1112
+      unsigned char* rows = reinterpret_cast<unsigned char*>(hc.data() + 238);
+      for (int c = 0; c < kM; c++) rows[c] = (unsigned char)(c % kN);
+      CU(cudaMalloc((void**)&ctx->casc_const, hc.size() * 8));
+      CU(cudaMemcpy(ctx->casc_const, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  const double* cG = ctx->casc_const;
+  const double* cg0 = cG + 196;
+  const double* cCIv = cG + 210;
+  const uint8_t* cCIr = reinterpret_cast<const uint8_t*>(cG + 238);
+  // workspace per scenario: doubles CE0 140 | ce00 10 | ci0 28 | x0 14 | f0 1 | CE2 14 | ce02 1 | CI2 392 | x2 14 | f2 1,
+  // floats goal2 1 | Z 196 | y 14, ints st0 | st2
+  const long long perD = 140 + 10 + 28 + 14 + 1 + 14 + 1 + 392 + 14 + 1, perF = 1 + 196 + 14, perI = 2;
+  const long long chunk_max = 1ll << 17;
+  for (long long q0 = 0; q0 < s->batch; q0 += chunk_max) {
+    const long long B = (s->batch - q0) < chunk_max ? (s->batch - q0) : chunk_max;
+    AsyncBuf ws;
+    ws.st = st;
+    CU(cudaMallocFromPoolAsync(&ws.p, (size_t)B * (perD * 8 + perF * 4 + perI * 4) + 256, ctx->pool, st));
+    double* d = static_cast<double*>(ws.p);
+    CascadeParams P;
+    memset(&P, 0, sizeof P);
+    P.batch = B;
+    P.q = s->q + q0 * 7; P.qd = s->qd + q0 * 7; P.M = s->M + q0 * 49; P.h = s->h + q0 * 7;
+    P.J = s->J + q0 * 21; P.Jd = s->Jd + q0 * 21;
+    P.pos_des = s->pos_des + q0 * 3; P.pos_cur = s->pos_cur + q0 * 3; P.vel_des = s->vel_des + q0 * 3;
+    P.vel_cur = s->vel_cur + q0 * 3; P.acc_des = s->acc_des + q0 * 3; P.acc_cur = s->acc_cur + q0 * 3;
+    P.q1_des = s->q1_des + q0;
+    P.kp_task = s->kp_task; P.kd_task = s->kd_task; P.kp_joint = s->kp_joint; P.kd_joint = s->kd_joint;
+    for (int i = 0; i < kDof; i++) {
+      P.acc_p[i] = s->acc_p[i]; P.acc_n[i] = s->acc_n[i]; P.tau_p[i] = s->tau_p[i]; P.tau_n[i] = s->tau_n[i];
+      P.q_sup[i] = s->q_sup[i]; P.q_inf[i] = s->q_inf[i];
+    }
+    P.joint_task = s->joint_task;
+    double* x0 = nullptr; double* f0 = nullptr; double* x2 = nullptr; double* f2 = nullptr;
+    P.CE0 = d; d += B * 140;
+    P.ce00 = d; d += B * 10;
+    P.ci0 = d; d += B * 28;
+    x0 = d; d += B * 14;
+    f0 = d; d += B;
+    P.CE2 = d; d += B * 14;
+    P.ce02 = d; d += B;
+    P.CI2 = d; d += B * 392;
+    x2 = d; d += B * 14;
+    f2 = d; d += B;
+    float* fl = reinterpret_cast<float*>(d);
+    P.goal2 = fl; fl += B;
+    P.Z = fl; fl += B * 196;
+    P.y = fl; fl += B * 14;
+    int* st0 = reinterpret_cast<int*>(fl);
+    int* st2 = st0 + B;
+    P.x0 = x0; P.f0 = f0; P.st0 = st0; P.x2 = x2; P.f2 = f2; P.st2 = st2;
+    P.tracking = s->tracking + q0 * kN; P.torques = s->torques + q0 * kDof;
+    P.status0 = s->status0 ? s->status0 + q0 : nullptr;
+    P.status2 = s->status2 ? s->status2 + q0 : nullptr;
+    const unsigned blocks = (unsigned)((B + 127) / 128);
+    cascade_assemble_kernel<<<blocks, 128, 0, st>>>(P);
+    g_launches.fetch_add(1);
+    mgqp_batch l0;
+    memset(&l0, 0, sizeof l0);
+    l0.n = kN; l0.p = kP0; l0.m = kM; l0.batch = B;
+    l0.G = cG; l0.g0 = cg0; l0.CE = P.CE0; l0.ce0 = P.ce00; l0.CI = nullptr; l0.ci0 = P.ci0;
+    l0.sG = 0; l0.sg0 = 0; l0.sCE = 140; l0.sce0 = 10; l0.sCI = 0; l0.sci0 = 28;
+    l0.CI_val = cCIv; l0.CI_row = cCIr; l0.sCIv = 0; l0.sCIr = 0;
+    l0.x = x0; l0.f = f0; l0.status = st0;
+    l0.flags = MGQP_FLAG_RETRY_WITHOUT_CI;
+    if ((rc = solve_device(&l0, device, st))) return rc;
+    // (64 threads: 64 x 140 floats of working matrices stay under the 48 KB a launch may ask for unannounced)
+    cascade_project_kernel<<<(unsigned)((B + 63) / 64), 64, 64 * kN * kP0 * sizeof(float), st>>>(P);
+    g_launches.fetch_add(1);
+    {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(MGQP_ERR_CUDA, "cascade_project_kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    mgqp_batch l2;
+    memset(&l2, 0, sizeof l2);
+    l2.n = kN; l2.p = 1; l2.m = kM; l2.batch = B;
+    l2.G = cG; l2.g0 = cg0; l2.CE = P.CE2; l2.ce0 = P.ce02; l2.CI = P.CI2; l2.ci0 = P.ci0;
+    l2.sG = 0; l2.sg0 = 0; l2.sCE = 14; l2.sce0 = 1; l2.sCI = 392; l2.sci0 = 28;
+    l2.x = x2; l2.f = f2; l2.status = st2;
+    l2.flags = MGQP_FLAG_RETRY_WITHOUT_CI;
+    if ((rc = solve_device(&l2, device, st))) return rc;
+    cascade_finish_kernel<<<blocks, 128, 0, st>>>(P);
+    g_launches.fetch_add(1);
+    if (s->tap_CE0) CU(cudaMemcpyAsync(s->tap_CE0 + q0 * 140, P.CE0, (size_t)B * 140 * 8, cudaMemcpyDeviceToDevice, st));
+    if (s->tap_ce0) CU(cudaMemcpyAsync(s->tap_ce0 + q0 * 10, P.ce00, (size_t)B * 10 * 8, cudaMemcpyDeviceToDevice, st));
+    if (s->tap_ci0) CU(cudaMemcpyAsync(s->tap_ci0 + q0 * 28, P.ci0, (size_t)B * 28 * 8, cudaMemcpyDeviceToDevice, st));
+    if (s->tap_Z) CU(cudaMemcpyAsync(s->tap_Z + q0 * 196, P.Z, (size_t)B * 196 * 4, cudaMemcpyDeviceToDevice, st));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MGQP_ERR_CUDA, "cascade kernels failed: %s", cudaGetErrorString(e));
+  }
+  return MGQP_OK;
+}
+
+// host pointers: upload the state of a chunk, run the cascade, download the answers; two streams alternate
+int cascade_host(const mgqp_scenarios* h, int device, long long chunk) {
+  if (!h || h->batch < 0) return fail(MGQP_ERR_INVALID_ARG, "bad scenario descriptor");
+  if (h->batch == 0) return MGQP_OK;
+  DeviceCtx* ctx = nullptr;
+  int rc = device_ctx(device, &ctx);
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  if (chunk <= 0) chunk = 1 << 16;
+  if (chunk > h->batch) chunk = h->batch;
+  std::lock_guard<std::mutex> host_lock(ctx->host_mu);
+  const int inF[13] = {7, 7, 49, 7, 21, 21, 3, 3, 3, 3, 3, 3, 1};
+  const float* const src[13] = {h->q, h->qd, h->M, h->h, h->J, h->Jd, h->pos_des, h->pos_cur, h->vel_des,
+                                h->vel_cur, h->acc_des, h->acc_cur, h->q1_des};
+  long long in_floats = 0;
+  for (int k = 0; k < 13; k++) in_floats += inF[k];
+  const size_t need = (size_t)chunk * (in_floats * 4 + 14 * 4 + 7 * 4 + 8) + 16 * 256;
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->casc_st[i]) CU(cudaStreamCreateWithFlags(&ctx->casc_st[i], cudaStreamNonBlocking));
+    if (ctx->casc_cap[i] < need) {
+      if (ctx->casc_arena[i]) CU(cudaFree(ctx->casc_arena[i]));
+      ctx->casc_arena[i] = nullptr; ctx->casc_cap[i] = 0;
+      CU(cudaMalloc(&ctx->casc_arena[i], need));
+      ctx->casc_cap[i] = need;
+    }
+  }
+  g_h2d_bytes = g_d2h_bytes = 0;
+  int k = 0;
+  for (long long q0 = 0; q0 < h->batch && !rc; q0 += chunk, k++) {
+    const long long B = (h->batch - q0) < chunk ? (h->batch - q0) : chunk;
+    cudaStream_t st = ctx->casc_st[k & 1];
+    CU(cudaStreamSynchronize(st));
+    char* base = static_cast<char*>(ctx->casc_arena[k & 1]);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 255) & ~(size_t)255; return p; };
+    mgqp_scenarios d = *h;
+    d.batch = B;
+    const float* dev_in[13];
+    for (int f = 0; f < 13; f++) {
+      float* p = reinterpret_cast<float*>(take((size_t)B * inF[f] * 4));
+      CU(cudaMemcpyAsync(p, src[f] + q0 * inF[f], (size_t)B * inF[f] * 4, cudaMemcpyHostToDevice, st));
+      dev_in[f] = p;
+      g_h2d_bytes += B * inF[f] * 4;
+    }
+    d.q = dev_in[0]; d.qd = dev_in[1]; d.M = dev_in[2]; d.h = dev_in[3]; d.J = dev_in[4]; d.Jd = dev_in[5];
+    d.pos_des = dev_in[6]; d.pos_cur = dev_in[7]; d.vel_des = dev_in[8]; d.vel_cur = dev_in[9];
+    d.acc_des = dev_in[10]; d.acc_cur = dev_in[11]; d.q1_des = dev_in[12];
+    d.tracking = reinterpret_cast<float*>(take((size_t)B * 14 * 4));
+    d.torques = reinterpret_cast<float*>(take((size_t)B * 7 * 4));
+    d.status0 = h->status0 ? reinterpret_cast<int32_t*>(take((size_t)B * 4)) : nullptr;
+    d.status2 = h->status2 ? reinterpret_cast<int32_t*>(take((size_t)B * 4)) : nullptr;
+    d.tap_CE0 = nullptr; d.tap_ce0 = nullptr; d.tap_ci0 = nullptr; d.tap_Z = nullptr;
+    if ((rc = cascade_device(&d, device, st))) break;
+    CU(cudaMemcpyAsync(h->tracking + q0 * 14, d.tracking, (size_t)B * 14 * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->torques + q0 * 7, d.torques, (size_t)B * 7 * 4, cudaMemcpyDeviceToHost, st));
+    g_d2h_bytes += B * 21 * 4;
+    if (h->status0) { CU(cudaMemcpyAsync(h->status0 + q0, d.status0, (size_t)B * 4, cudaMemcpyDeviceToHost, st)); g_d2h_bytes += B * 4; }
+    if (h->status2) { CU(cudaMemcpyAsync(h->status2 + q0, d.status2, (size_t)B * 4, cudaMemcpyDeviceToHost, st)); g_d2h_bytes += B * 4; }
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaError_t e = cudaStreamSynchronize(ctx->casc_st[i]);
+    if (e != cudaSuccess && !rc) rc = fail(MGQP_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
 }  // namespace
 
 // ====================================================================== exported C ABI
@@ -790,6 +976,16 @@ int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int nd
   for (int i = 0; i < ndev; i++)
     if (rcs[i]) return fail(rcs[i], "device %d: %s", devices[i], errs[i].c_str());
   return MGQP_OK;
+}
+
+int mgqp_cascade_batched(const mgqp_scenarios* s, int device, void* stream) {
+  DeviceGuard guard;
+  return cascade_device(s, device, static_cast<cudaStream_t>(stream));
+}
+
+int mgqp_cascade_batched_host(const mgqp_scenarios* s, int device, int64_t chunk) {
+  DeviceGuard guard;
+  return cascade_host(s, device, chunk);
 }
 
 int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const double* g0, const double* CE,

@@ -239,6 +239,52 @@ def make_shipped(B: int, level: int = 0, seed: int | None = None) -> QPBatch:
     return QPBatch(name, n, p, m, _f32(G), _f32(g0), _f32(CE), _f32(ce0), _f32(CI), _f32(ci0))
 
 
+# Gains (src/mgqp.cpp:104-110) and limits (ops/mgqp.ops:132-134, :187-189) of the 7-DoF deployment as shipped
+SHIPPED_CONFIG = dict(
+    kp_task=np.float32(100.0), kd_task=np.float32(25.0), kp_joint=np.float32(200.0), kd_joint=np.float32(100.0),
+    acc_p=np.full(7, 5.0, np.float32), acc_n=np.full(7, -5.0, np.float32),
+    tau_p=np.full(7, 100.0, np.float32), tau_n=np.full(7, -100.0, np.float32),
+    q_sup=np.array([0.8, 1.5, 2.5, 1.5, 3.0, 1.5, 3.0], np.float32),
+    q_inf=-np.array([0.8, 1.5, 2.5, 1.5, 3.0, 1.5, 3.0], np.float32),
+    joint_task=0,
+)
+# the same wiring with the wide joint range the deployment script uses for its other robot (ops/mgqp.ops:190-195):
+# with the shipped +-0.8 rad on joint 1 the log-barrier bounds always contradict each other and every level ends in
+# solveNextStep's retry ("the problem seems never feasible", src/mgqp.cpp:716); here most levels are feasible
+WIDE_CONFIG = dict(SHIPPED_CONFIG, q_sup=np.full(7, 3.1415927, np.float32), q_inf=np.full(7, -3.1415927, np.float32))
+SCENARIO_FIELDS = ("q", "qd", "M", "h", "J", "Jd", "pos_des", "pos_cur", "vel_des", "vel_cur", "acc_des", "acc_cur",
+                   "q1_des")
+
+
+def make_scenarios(B: int, seed: int = 4321, config=None, scale: float = 1.0):
+    """Seeded robot states around the shipped set-up (float32): joint angles inside the limits (some close to
+    them, so that the log barrier bites), SPD inertia, a translation Jacobian, targets a few cm away.
+    `scale` shrinks tracking errors and velocities: with small ones (0.01) and WIDE_CONFIG the demanded
+    accelerations fit the box limits and the levels are feasible, otherwise most levels end in the retry."""
+    rng = np.random.default_rng(seed)
+    cfg = SHIPPED_CONFIG if config is None else config
+    f32 = np.float32
+    span = cfg["q_sup"] - cfg["q_inf"]
+    u = rng.uniform(0.02, 0.98, (B, 7))
+    near = rng.random((B, 7)) < 0.1
+    u = np.where(near, rng.choice([0.0005, 0.9995], (B, 7)), u)
+    q = (cfg["q_inf"] + span * u).astype(f32)
+    H = rng.standard_normal((B, 7, 7))
+    Mq = (0.3 * np.einsum("bki,bkj->bij", H, H) / 7 + np.eye(7) * rng.uniform(0.5, 3.0, (B, 1, 1))).astype(f32)
+    s = dict(
+        q=q, qd=(0.5 * scale * rng.standard_normal((B, 7))).astype(f32), M=Mq,
+        h=(5.0 * rng.standard_normal((B, 7))).astype(f32),
+        J=(0.4 * rng.standard_normal((B, 3, 7))).astype(f32), Jd=(0.2 * rng.standard_normal((B, 3, 7))).astype(f32),
+        pos_des=rng.uniform(-0.5, 0.5, (B, 3)).astype(f32), vel_des=(0.1 * scale * rng.standard_normal((B, 3))).astype(f32),
+        acc_des=(0.1 * scale * rng.standard_normal((B, 3))).astype(f32),
+        vel_cur=(0.1 * scale * rng.standard_normal((B, 3))).astype(f32),
+        acc_cur=(0.1 * scale * rng.standard_normal((B, 3))).astype(f32),
+    )
+    s["q1_des"] = (q[:, cfg["joint_task"]] + 0.3 * scale * rng.standard_normal(B)).astype(f32)
+    s["pos_cur"] = (s["pos_des"] + 0.05 * scale * rng.standard_normal((B, 3))).astype(f32)
+    return s
+
+
 def make_random(B: int, n: int, p: int, m: int, seed: int = 0, box: bool = False) -> QPBatch:
     """Generic dense random QPs of any shape (shape-generic parity tests)."""
     rng = np.random.default_rng(seed)
