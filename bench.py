@@ -342,6 +342,64 @@ def c1_latency_record(mgqp_b200):
     return rec
 
 
+def cascade_record(mgqp_b200, dev):
+    """the solver's two callers batched -- on-device QP assembly (updateHook) and the priority
+    cascade (solveNextHierarchy) of the shipped 7-DoF wiring, from ~0.5 KB of robot state per scenario.  One
+    cascade = two levels, each a solve plus (where the level is infeasible) solveNextStep's retry."""
+    import torch
+    from mgqp_b200 import workloads
+    from oracle import cascade_oracle as co, oracle_py
+    rec = {}
+    B = 400_000
+    for name, cfg, scale in (("shipped", workloads.SHIPPED_CONFIG, 1.0), ("wide_limits", workloads.WIDE_CONFIG, 0.01)):
+        s = workloads.make_scenarios(B, config=cfg, scale=scale)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
+        r = mgqp_b200.solve_cascade_batched(t, cfg, taps=True)
+        torch.cuda.synchronize()
+        l0 = mgqp_b200.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            mgqp_b200.solve_cascade_batched(t, cfg)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        launches = (mgqp_b200.kernel_launch_count() - l0) // 3
+        sp = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in s.items()}
+        mgqp_b200.solve_cascade_batched_host(sp, cfg, device=dev.index or 0)
+        t0 = time.perf_counter()
+        h = mgqp_b200.solve_cascade_batched_host(sp, cfg, device=dev.index or 0)
+        e2e_s = time.perf_counter() - t0
+        up, down = mgqp_b200.last_transfer_bytes()
+        # parity on a sample: the restatement fed with the device's own projector / barrier limits must agree bit for bit
+        ns = 4000
+        sub = {k: v[:ns] for k, v in s.items()}
+        exp = co.cascade(oracle_py.restatement(), sub, cfg, threads=host_threads(), Z_override=r.Z[:ns].cpu().numpy(),
+                         limits_override=r.ci0[:ns].cpu().numpy().astype(np.float32))
+        t0 = time.perf_counter()
+        co.cascade(oracle_py.restatement(), sub, cfg, threads=host_threads())
+        cpu_s = time.perf_counter() - t0
+        st0 = r.status0.cpu().numpy()
+        rec[name] = {"scenarios": B, "value": B / (ms / 1e3), "unit": "cascades/s", "ms_per_step": ms,
+                     "kernel_launches_per_step": int(launches),
+                     "level0_retried_frac": float(((st0 & 16) != 0).mean()),
+                     "e2e": {"value": B / e2e_s, "unit": "cascades/s", "h2d_bytes_per_step": int(up),
+                             "d2h_bytes_per_step": int(down), "matches_device_leg": bool(np.array_equal(
+                                 h.tracking, r.tracking.cpu().numpy()))},
+                     "parity_check": {"sample": ns, "tracking_bit_identical": bool(np.array_equal(
+                         r.tracking[:ns].cpu().numpy(), exp["tracking"])),
+                         "torques_bit_identical": bool(np.array_equal(r.torques[:ns].cpu().numpy(), exp["torques"])),
+                         "status_equal": bool(np.array_equal(st0[:ns], exp["status0"])),
+                         "oracle": "oracle/cascade_oracle.py fed with the device's projector Z (parity unpinned "
+                                   "against Eigen: see that file)"},
+                     "cpu_baseline": {"value": ns / cpu_s, "unit": "cascades/s", "cores": host_threads(), "kind": "port",
+                                      "sample": f"{ns} scenarios: numpy float32 assembly + LAPACK SVD + the -O2 solver "
+                                                "restatement on all host threads"}}
+        del t, r
+        torch.cuda.empty_cache()
+    return rec
+
+
 def c5_sharded_record(mgqp_b200, dev, rank, world, dist):
     """BASELINE.json configs[4]: a 10M-QP sweep with mixed feasible / infeasible instances, STRONG-scaled: the same
     10M QPs are split by QP index over the ranks (one GPU each, no data-path collective).  Every rank's shard is a
@@ -568,6 +626,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             configs["C4"] = c4_record(mgqp_b200, dev, peak, C4_FULL)
         except Exception as e:
             configs["C4"] = {"error": repr(e)}
+        try:
+            configs["cascade"] = cascade_record(mgqp_b200, dev)
+        except Exception as e:
+            configs["cascade"] = {"error": repr(e)}
         try:
             configs["C1_latency"] = c1_latency_record(mgqp_b200)
         except Exception as e:

@@ -23,6 +23,9 @@
 // Control flow is uniform across the CTA: thread 0's decisions are broadcast through shared memory.
 #pragma once
 #include "gi_lane.cuh"  // LaneIO, ln_distance, MGQP_LDG, MGQP_EPS
+#ifndef MGQP_EMULATE
+#include "gi_large_dmma.cuh"
+#endif
 
 #ifdef MGQP_EMULATE
 #define MGQP_UNROLL8
@@ -42,6 +45,9 @@
 namespace mgqp {
 
 #define MGQP_ROWBLK 8
+#ifndef MGQP_ELL_K
+#define MGQP_ELL_K 64
+#endif
 
 struct LargeView {
   int n, p, m, T;
@@ -50,7 +56,8 @@ struct LargeView {
   int oredi, oA, oAold;   // ints, byte offsets
   int oact, oexcl, oskip; // bytes, byte offsets
   int smem_bytes;
-  long long ws_doubles;   // global workspace per CTA: Gc | J | R | s
+  int ell_k;              // capacity of the ELL form of CI (nonzeros kept per column)
+  long long ws_doubles;   // global workspace per CTA: Gc | J | R | s | ELL values | ELL rows | nnz per column
 };
 
 MGQP_HOST inline LargeView make_large_view(int n, int p, int m, int T) {
@@ -80,12 +87,21 @@ MGQP_HOST inline LargeView make_large_view(int n, int p, int m, int T) {
   v.oexcl = b; b += m;
   v.oskip = b; b += n + 1;
   v.smem_bytes = (b + 15) & ~15;
-  v.ws_doubles = 3ll * n * n + m;
+  // + the inequality block in ELL form: up to MGQP_ELL_K (value, row) pairs per column, [k][column] so that the
+  //   threads of the scan (one column each) read consecutive addresses; nnz per column behind it
+  v.ell_k = n < MGQP_ELL_K ? n : MGQP_ELL_K;
+  v.ws_doubles = 3ll * n * n + m + (long long)v.ell_k * m + ((long long)v.ell_k * m + 3) / 4 + (m + 3) / 4 + 2;
   return v;
 }
 
 struct LargeOut {
   double* x; double* f; int* status; int* iq; int* A; int* iters;
+  // Admission gate of the set-up phase (device build only; null = none).  The factorisation streams its n*n
+  // matrices n/3 times; with every resident CTA in that phase at once (hundreds of MB) nothing survives in L2 and
+  // each pass comes from DRAM.  At most gate_limit CTAs factorise at a time, so that their matrices stay L2-resident;
+  // the others wait here (the SM's second CTA keeps iterating meanwhile).
+  unsigned* gate = nullptr;
+  int gate_limit = 0;
 };
 
 template <bool FMA>
@@ -119,6 +135,14 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   double* J = Gc + (size_t)n * n;
   double* R = J + (size_t)n * n;
   double* sg = R + (size_t)n * n;  // s[m], only read back on the rare exact-psi path
+  // CI in ELL form (built by the one compulsory pass over the dense block): the scan of an MPC-style constraint
+  // matrix -- bounds on accelerations, velocities, positions: identity and integrator blocks, a few percent
+  // nonzeros -- then reads the nonzeros instead of 8*n*m bytes per iteration
+  const int EK = v.ell_k;
+  double* ell_val = sg + m;
+  unsigned short* ell_row = reinterpret_cast<unsigned short*>(ell_val + (size_t)EK * m);
+  unsigned short* ell_nnz = ell_row + (((size_t)EK * m + 3) & ~(size_t)3);
+  constexpr unsigned short ELL_DENSE = 0xffff;  // more than EK nonzeros: this column is scanned densely
   const double INF = d_inf();
   constexpr int NONE = 0x7fffffff;
 
@@ -218,6 +242,82 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   double f = 0.0;
 
   // ---------------------------------------------------------------- set-up
+#ifndef MGQP_EMULATE
+  if (out.gate) {
+    if (tid == 0) {
+      while (atomicAdd(out.gate, 1u) >= (unsigned)out.gate_limit) {
+        atomicSub(out.gate, 1u);
+        __nanosleep(4000);
+      }
+    }
+    blk_sync();
+  }
+#endif
+  bool fail = false;
+  double c1 = 0.0, c2 = 0.0, R_norm = 1.0;
+  bool dense_done = false;
+#ifndef MGQP_EMULATE
+  if (FMA && n >= 128) {
+    // MGQP_FLAG_FAST_MATH: the dense set-up on the fp64 tensor cores (gi_large_dmma.cuh)
+    dense_done = true;
+    MGQP_UNROLL1
+    for (int e = tid; e < n * n; e += T) R[e] = 0.0;
+    if (tid == 0) {
+      double c = 0.0;
+      MGQP_UNROLL1
+      for (int i = 0; i < n; i++) c = d_add(c, MGQP_LDG(io.G + (size_t)i * n + i));
+      sbc[0] = c;
+    }
+    blk_sync();
+    c1 = sbc[0];
+    blk_sync();
+    double bad = 0.0;
+    if (tid == 0) sbc[2] = 0.0;
+    const bool okf = large_setup_dmma(n, io.G, Gc, J, srow, &sbc[2]);
+    blk_sync();
+    if (!okf) {
+      fail = true;
+      status = 2;
+      f = sbc[2];
+    } else {
+      // y = X g0 (row i of X is contiguous), x0 = -X' y (column j: coalesced), f = 0.5 g0.x0, c2 = trace(J) = trace(X)
+      MGQP_UNROLL1
+      for (int i = tid; i < n; i += T) {
+        double a = 0.0;
+        const double* Xi = J + (size_t)i * n;
+        MGQP_UNROLL8
+        for (int j = 0; j <= i; j++) a = d_fma(Xi[j], MGQP_LDG(io.g0 + j), a);
+        sz[i] = a;
+      }
+      blk_sync();
+      MGQP_UNROLL1
+      for (int j = tid; j < n; j += T) {
+        double a = 0.0;
+        MGQP_UNROLL8
+        for (int i = j; i < n; i++) a = d_fma(J[(size_t)i * n + j], sz[i], a);
+        sx[j] = -a;
+      }
+      blk_sync();
+      if (tid == 0) {
+        double t = 0.0, fs = 0.0;
+        MGQP_UNROLL1
+        for (int i = 0; i < n; i++) {
+          t = d_add(t, J[(size_t)i * n + i]);
+          fs = d_fma(MGQP_LDG(io.g0 + i), sx[i], fs);
+        }
+        sbc[0] = t;
+        sbc[1] = d_mul(0.5, fs);
+      }
+      blk_sync();
+      c2 = sbc[0];
+      f = sbc[1];
+      blk_sync();
+    }
+    (void)bad;
+  }
+#endif
+  bool my_nonfinite = false;  // this thread wrote a factor entry that is inf or NaN
+  if (!dense_done) {
   MGQP_UNROLL1
   for (int e = tid; e < n * n; e += T) Gc[e] = MGQP_LDG(io.G + e);
   MGQP_UNROLL1
@@ -230,12 +330,10 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     sbc[0] = c;
   }
   blk_sync();
-  const double c1 = sbc[0];
+  c1 = sbc[0];
   blk_sync();
 
   // Cholesky, row-oriented as the reference; row i is staged in sz for the broadcast operand
-  bool fail = false;
-  bool my_nonfinite = false;  // this thread wrote a factor entry that is inf or NaN
   MGQP_UNROLL1
   for (int i = 0; i < n && !fail; i++) {
     MGQP_UNROLL1
@@ -274,8 +372,8 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     blk_sync();
   }
 
-  double c2 = 0.0, R_norm = 1.0;
-  if (!fail) {
+  }  // !dense_done: Cholesky
+  if (!fail && !dense_done) {
     // J = L^-T: thread i owns row i = forward_elimination(L, e_i).  J is upper triangular: with a
     // finite factor the entries left of the diagonal are exactly +0.0 and the products they enter
     // are +-0.0, which never change the accumulator (x - (+-0) = x, and +0.0 - (+-0.0) = +0.0), so the
@@ -423,8 +521,32 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int k = tid; k < n; k += T) {
       double* Jk = J + k;  // row k of J, element j at Jk[j * n]: coalesced across the threads
       double t2 = Jk[(size_t)(n - 1) * n];
-      MGQP_UNROLL8
-      for (int j = n - 1; j >= iq + 1; j--) {
+      // The original entries J[k][j-1] do not depend on the rotations: they are fetched eight columns ahead of
+      // their use.  (Written as one load and one store per trip, the loop waited a full memory round trip per
+      // rotation -- ~300 of them per sweep: the stores to the same array keep the compiler from hoisting the loads.)
+      constexpr int GB = 8;
+      int j = n - 1;
+      MGQP_UNROLL1
+      for (; j - GB >= iq; j -= GB) {
+        double t1v[GB];
+#pragma unroll
+        for (int u = 0; u < GB; u++) t1v[u] = Jk[(size_t)(j - 1 - u) * n];
+#pragma unroll
+        for (int u = 0; u < GB; u++) {
+          const int jj = j - u;
+          const double t1 = t1v[u];
+          if (!skip[jj]) {
+            const double n1 = d_add(d_mul(t1, scc[jj]), d_mul(t2, sss[jj]));
+            Jk[(size_t)jj * n] = d_sub(d_mul(sh[jj], d_add(t1, n1)), t2);
+            t2 = n1;
+          } else {
+            Jk[(size_t)jj * n] = t2;
+            t2 = t1;
+          }
+        }
+      }
+      MGQP_UNROLL1
+      for (; j >= iq + 1; j--) {
         const double t1 = Jk[(size_t)(j - 1) * n];
         if (!skip[j]) {
           const double n1 = d_add(d_mul(t1, scc[j]), d_mul(t2, sss[j]));
@@ -532,6 +654,12 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     }
   };
 
+#ifndef MGQP_EMULATE
+  if (out.gate) {
+    blk_sync();
+    if (tid == 0) atomicSub(out.gate, 1u);
+  }
+#endif
   bool done = fail;
 
   // ---------------------------------------------------------------- equality constraints
@@ -568,6 +696,34 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   // ---------------------------------------------------------------- active-set iteration
   MGQP_UNROLL1
   for (int i = tid; i < m; i += T) act[i] = 0;
+  // ELL form of CI: one pass over the dense block (thread = column, coalesced along the rows).  A zero
+  // coefficient contributes +-0.0 to a sum that starts at +0.0 and can never become -0.0: leaving it out does not
+  // change a bit of s_i as long as x is finite (0 * inf would be NaN); NaN coefficients count as nonzeros.
+  bool any_sparse = false;
+  if (!done && m > 0 && n <= 0xfffe) {
+    MGQP_UNROLL1
+    for (int i = tid; i < m; i += T) {
+      int cnt = 0;
+      MGQP_UNROLL4
+      for (int j = 0; j < n; j++) {
+        const double a = MGQP_LDG(io.CI + (size_t)j * m + i);
+        if (a != 0.0) {
+          if (cnt < EK) {
+            ell_val[(size_t)cnt * m + i] = a;
+            ell_row[(size_t)cnt * m + i] = (unsigned short)j;
+          }
+          cnt++;
+        }
+      }
+      ell_nnz[i] = (cnt <= EK) ? (unsigned short)cnt : ELL_DENSE;
+      any_sparse = any_sparse || (cnt <= EK && 4 * cnt <= n);
+    }
+    if (tid == 0) sredi[0] = 0;
+    blk_sync();
+    if (any_sparse) sredi[0] = 1;
+    blk_sync();
+    any_sparse = sredi[0] != 0;
+  }
   blk_sync();
   const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
   int ip = 0;
@@ -586,6 +742,61 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
       }
       double best = ss, psi = 0.0;
       int bidx = NONE;
+      // the ELL form needs a finite x (see above); a poisoned iterate takes the dense scan
+      bool sparse_scan = any_sparse;
+      if (sparse_scan) {
+        bool bad = false;
+        MGQP_UNROLL1
+        for (int j = tid; j < n; j += T) bad = bad || !(d_abs(sx[j]) < INF);
+        if (tid == 0) sredi[0] = 0;
+        blk_sync();
+        if (bad) sredi[0] = 1;
+        blk_sync();
+        sparse_scan = sredi[0] == 0;
+        blk_sync();
+      }
+      if (sparse_scan) {
+        MGQP_UNROLL1
+        for (int i0 = tid; i0 < m; i0 += 4 * T) {
+          // four columns per thread at a time: four independent accumulation chains
+          double acc[4] = {0.0, 0.0, 0.0, 0.0};
+          int cnt[4], col[4];
+          int kmax = 0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            col[c] = i0 + c * T;
+            cnt[c] = (col[c] < m) ? (int)ell_nnz[col[c]] : 0;
+            if (cnt[c] == (int)ELL_DENSE) {  // dense column: the reference's full sum
+              double a = 0.0;
+              MGQP_UNROLL4
+              for (int j = 0; j < n; j++) a = mad<FMA>(MGQP_LDG(io.CI + (size_t)j * m + col[c]), sx[j], a);
+              acc[c] = a;
+              cnt[c] = 0;
+            }
+            kmax = cnt[c] > kmax ? cnt[c] : kmax;
+          }
+          MGQP_UNROLL1
+          for (int k = 0; k < kmax; k++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+              if (k < cnt[c])
+                acc[c] = mad<FMA>(ell_val[(size_t)k * m + col[c]], sx[ell_row[(size_t)k * m + col[c]]], acc[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int i = col[c];
+            if (i < m) {
+              const double sum = d_add(acc[c], MGQP_LDG(io.ci0 + i));
+              sg[i] = sum;
+              if (sum < 0.0) psi = d_add(psi, sum);
+              if (sum < best && !act[i] && excl[i]) {
+                best = sum;
+                bidx = i;
+              }
+            }
+          }
+        }
+      } else
       MGQP_UNROLL1
       for (int i0 = tid; i0 < m; i0 += 4 * T) {
         // up to four columns per thread at a time: four independent accumulation chains

@@ -14,6 +14,8 @@ struct LargeParams {
   int max_iter;
   unsigned* ticket;
   double* workspace;  // gridDim.x * v.ws_doubles
+  unsigned* gate;     // admission counter of the set-up phase (zeroed before the launch) or null
+  int gate_limit;
   const unsigned long long* batch_dev;  // if set: the number of QPs lives on the device (<= batch)
 };
 
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(512, 1) gi_large_kernel(const __grid_constant_
     out.iq = P.iq ? P.iq + q : nullptr;
     out.A = P.A ? P.A + q * (long long)(P.v.p + P.v.m) : nullptr;
     out.iters = P.iters ? P.iters + q : nullptr;
+    out.gate = P.gate;
+    out.gate_limit = P.gate_limit;
     gi_large_solve<FMA>(P.v, smem_raw, ws, io, P.max_iter, out);
   }
 }

@@ -304,6 +304,22 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
   void* ws = nullptr;
   CU(cudaMallocFromPoolAsync(&ws, (size_t)(ctas * ws_bytes), ctx->pool, st));
   P.workspace = static_cast<double*>(ws);
+  // set-up admission gate (gi_large.cuh): off by default -- measured on C4 (profiles/r02_notes.md): limiting the
+  // number of CTAs that factorise at once to what fits L2 costs more in waiting than it saves in DRAM latency
+  {
+    long long limit = 0;
+    if (const char* e = std::getenv("MGQP_LARGE_SETUP_GATE")) limit = std::atoll(e);  // tuning knob (0 = off)
+    if (limit >= 1 && limit < ctas) {
+      unsigned slot;
+      {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        slot = ctx->ring_pos++ % kTicketRing;
+      }
+      P.gate = ctx->tickets + slot;
+      P.gate_limit = (int)limit;
+      CU(cudaMemsetAsync(P.gate, 0, sizeof(unsigned), st));
+    }
+  }
   kern<<<(unsigned)ctas, lp.T, lp.v.smem_bytes, st>>>(P);
   g_launches.fetch_add(1);
   cudaError_t e = cudaGetLastError();

@@ -74,3 +74,16 @@ def test_poisoned_factor_takes_the_full_loops(emu_lib, restatement):
     assert np.array_equal(got["x"][keep], ref["x"][keep], equal_nan=True)
     assert np.array_equal(got["f"], ref["f"], equal_nan=True)
     assert np.array_equal(got["iters"][keep], ref["iters"][keep])
+
+
+def test_horizon_stacked_structure_uses_the_sparse_scan(emu_lib, restatement):
+    """The C4 construction (identity and integrator blocks: a few nonzeros per column) at a size the emulator can
+    run: the ELL form of CI must give bit-identical scans, also with -0.0 / NaN coefficients and a poisoned iterate."""
+    b = workloads.make_c4(6, seed=5, dof=3, steps=14)          # n = 42, m = 252
+    b.CI[1, 4, 7] = -0.0
+    b.CI[2, 5, 9] = np.nan
+    b.g0[3, 2] = np.inf                                        # x0 is not finite: the scan falls back to the dense sums
+    assert_bit_identical(large_solve(emu_lib, b), _oracle(restatement, b), "mpc")
+    b = workloads.make_c4(4, seed=6, dof=7, steps=12)          # n = 84 > 64: columns with more than 64 nonzeros stay dense
+    b.CI[:, :, 5] = np.random.default_rng(1).standard_normal((4, 84))
+    assert_bit_identical(large_solve(emu_lib, b, nthreads=128), _oracle(restatement, b), "mpc84")
