@@ -29,10 +29,12 @@
 
 #ifdef MGQP_EMULATE
 #define MGQP_UNROLL8
+#define MGQP_UNROLL16
 #define MGQP_UNROLL4
 #define MGQP_UNROLL_SETUP
 #else
 #define MGQP_UNROLL8 _Pragma("unroll 8")
+#define MGQP_UNROLL16 _Pragma("unroll 16")
 #define MGQP_UNROLL4 _Pragma("unroll 4")
 #ifndef MGQP_SETUP_DEPTH
 #define MGQP_SETUP_DEPTH 8
@@ -449,7 +451,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     MGQP_UNROLL1
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
-      MGQP_UNROLL8
+      MGQP_UNROLL16
       for (int j = 0; j < n; j++) s = mad<FMA>(J[(size_t)i * n + j], snp[j], s);  // J[j][i]
       sd[i] = s;
     }
@@ -458,7 +460,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
       const double* Ji = J + i;
-      MGQP_UNROLL8
+      MGQP_UNROLL16
       for (int j = iq; j < n; j++) s = mad<FMA>(Ji[(size_t)j * n], sd[j], s);  // J[i][j]
       sz[i] = s;
     }
@@ -521,10 +523,10 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int k = tid; k < n; k += T) {
       double* Jk = J + k;  // row k of J, element j at Jk[j * n]: coalesced across the threads
       double t2 = Jk[(size_t)(n - 1) * n];
-      // The original entries J[k][j-1] do not depend on the rotations: they are fetched eight columns ahead of
+      // The original entries J[k][j-1] do not depend on the rotations: they are fetched sixteen columns ahead of
       // their use.  (Written as one load and one store per trip, the loop waited a full memory round trip per
       // rotation -- ~300 of them per sweep: the stores to the same array keep the compiler from hoisting the loads.)
-      constexpr int GB = 8;
+      constexpr int GB = 16;
       int j = n - 1;
       MGQP_UNROLL1
       for (; j - GB >= iq; j -= GB) {
@@ -775,12 +777,25 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
             }
             kmax = cnt[c] > kmax ? cnt[c] : kmax;
           }
+          // four nonzeros of each of the four columns per trip: 32 loads in flight (the lists live in L2 / DRAM)
           MGQP_UNROLL1
-          for (int k = 0; k < kmax; k++) {
+          for (int k0 = 0; k0 < kmax; k0 += 4) {
+            double vv[4][4];
+            int rr[4][4];
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-              if (k < cnt[c])
-                acc[c] = mad<FMA>(ell_val[(size_t)k * m + col[c]], sx[ell_row[(size_t)k * m + col[c]]], acc[c]);
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                const bool on = k0 + u < cnt[c];
+                const size_t at = (size_t)(k0 + u) * m + col[c];
+                vv[u][c] = on ? ell_val[at] : 0.0;
+                rr[u][c] = on ? (int)ell_row[at] : 0;
+              }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int c = 0; c < 4; c++)
+                if (k0 + u < cnt[c]) acc[c] = mad<FMA>(vv[u][c], sx[rr[u][c]], acc[c]);
           }
 #pragma unroll
           for (int c = 0; c < 4; c++) {
