@@ -572,6 +572,31 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.cuda.empty_cache()
         c5s = c5_sharded_record(mgqp_b200, dev, rank, world, dist)
         dev_in = None
+    # ---- the in-library multi-device path (N > 1): rank 0's host threads drive one stream pair per device through
+    # solve_quadprog_batched_multi while the other ranks wait; host buffers, chunks from one shared queue
+    multi = None
+    if world > 1 and not args.no_extras and name == "C2":
+        dist.barrier()
+        if rank == 0:
+            try:
+                ndev = min(world, torch.cuda.device_count())
+                hb = workloads.make("C5", 1_000_000)
+                hp = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in hb.fields()]
+                os.environ["MGQP_HOST_THREADS"] = str(host_threads())
+                devs = list(range(ndev))
+                r = mgqp_b200.solve_quadprog_batched_multi(*hp, devices=devs)      # warm: arenas, streams
+                t0 = time.perf_counter()
+                r = mgqp_b200.solve_quadprog_batched_multi(*hp, devices=devs, out=r)
+                dt = time.perf_counter() - t0
+                up, down = mgqp_b200.last_transfer_bytes()
+                multi = {"api": "solve_quadprog_batched_multi (one host thread + two streams per device, chunks from a "
+                                "shared atomic queue; no collective)", "devices": ndev, "workload": "C5: 1M QPs in pinned "
+                         "host buffers, ~10 % infeasible", "value": hb.batch / dt, "unit": "QP/s",
+                         "chunks_per_device": mgqp_b200.last_multi_chunks(), "h2d_bytes": int(up), "d2h_bytes": int(down),
+                         "status_counts": np.bincount(r.status & 15, minlength=5).tolist()}
+            except Exception as e:
+                multi = {"error": repr(e)}
+        dist.barrier()
     if rank != 0:
         return
     # ---- parity spot check + CPU baseline on a bounded sample of the same inputs (rank 0, N=1 only)
@@ -627,6 +652,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         line["parity_check"] = parity
     if c5s:
         line["c5_sharded"] = c5s
+    if multi:
+        line["multi_device_library"] = multi
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:

@@ -160,6 +160,10 @@ int mgqp_blocks_all_equal(const double* base, int64_t stride, int64_t size, int6
 /* Bytes the last host-buffer call of the calling thread moved over the host<->device link. */
 void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h);
 
+/* Chunks each device took in the calling thread's last solve_quadprog_batched_multi (the shared queue balances
+ * uneven work, e.g. the infeasible instances of a scenario sweep); returns the number of devices of that call. */
+int mgqp_last_multi_chunks(int64_t* counts, int max_devices);
+
 /* Introspection. */
 const char* mgqp_status_string(int status);
 const char* mgqp_last_error(void);        /* thread-local text of the last non-OK return        */

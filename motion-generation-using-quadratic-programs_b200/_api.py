@@ -29,7 +29,7 @@ __all__ = [
     "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
     "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL",
     "FLAG_NO_HOST_PACK", "FLAG_RETRY_WITHOUT_CI", "STATUS_RETRIED", "mgqp_batch", "pack_bound_columns", "last_transfer_bytes",
-    "mgqp_scenarios", "CascadeResult", "solve_cascade_batched", "solve_cascade_batched_host",
+    "last_multi_chunks", "mgqp_scenarios", "CascadeResult", "solve_cascade_batched", "solve_cascade_batched_host",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -172,6 +172,15 @@ def last_transfer_bytes():
     up, down = C.c_int64(0), C.c_int64(0)
     lib().mgqp_last_transfer_bytes(C.byref(up), C.byref(down))
     return up.value, down.value
+
+
+def last_multi_chunks():
+    """Chunks each device took in this thread's last solve_quadprog_batched_multi call."""
+    buf = (C.c_int64 * 16)()
+    lib().mgqp_last_multi_chunks.restype = C.c_int
+    lib().mgqp_last_multi_chunks.argtypes = [C.POINTER(C.c_int64), C.c_int]
+    n = lib().mgqp_last_multi_chunks(buf, 16)
+    return [int(buf[i]) for i in range(n)]
 
 
 def pack_bound_columns(CI, threads: int = 0):

@@ -31,6 +31,7 @@ using namespace mgqp;
 
 thread_local std::string g_last_error;
 thread_local long long g_h2d_bytes = 0, g_d2h_bytes = 0;  // of the calling thread's last host-buffer call
+thread_local std::vector<long long> g_multi_chunks;       // chunks each device of the last multi-device call took
 std::atomic<long long> g_launches{0};
 
 int fail(int rc, const char* fmt, ...) {
@@ -692,7 +693,8 @@ long long default_chunk(const mgqp_batch* h) {
 }
 
 // Pull chunks from `next` until the batch is exhausted; two streams, two buffer sets.
-int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long>* next, int ndev = 1) {
+int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long>* next, int ndev = 1,
+         long long* chunks_done = nullptr) {
   int rc = validate(h);
   if (rc) return rc;
   DeviceCtx* ctx = nullptr;
@@ -756,6 +758,7 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     if (cudaStreamSynchronize(st[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "stream sync failed"); break; }
     rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1], pack);
     k++;
+    if (chunks_done) ++*chunks_done;
   }
   for (int i = 0; i < 2; i++) {
     cudaError_t e = cudaStreamSynchronize(st[i]);
@@ -977,16 +980,18 @@ int solve_quadprog_batched_multi(const mgqp_batch* h, const int* devices, int nd
   std::atomic<long long> up(0), down(0);
   std::vector<int> rcs(ndev, 0);
   std::vector<std::string> errs(ndev);
+  std::vector<long long> chunks(ndev, 0);
   std::vector<std::thread> th;
   for (int i = 0; i < ndev; i++)
     th.emplace_back([&, i]() {
       g_h2d_bytes = g_d2h_bytes = 0;
-      rcs[i] = pump(h, devices[i], chunk, &next, ndev);
+      rcs[i] = pump(h, devices[i], chunk, &next, ndev, &chunks[i]);
       if (rcs[i]) errs[i] = g_last_error;
       up += g_h2d_bytes;
       down += g_d2h_bytes;
     });
   for (auto& t : th) t.join();
+  g_multi_chunks = chunks;
   g_h2d_bytes = up.load();
   g_d2h_bytes = down.load();
   for (int i = 0; i < ndev; i++)
@@ -1092,6 +1097,12 @@ const char* mgqp_last_error(void) { return g_last_error.c_str(); }
 void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h) {
   if (h2d) *h2d = g_h2d_bytes;
   if (d2h) *d2h = g_d2h_bytes;
+}
+
+int mgqp_last_multi_chunks(int64_t* counts, int max_devices) {
+  const int n = (int)g_multi_chunks.size();
+  for (int i = 0; i < n && i < max_devices; i++) counts[i] = g_multi_chunks[i];
+  return n;
 }
 
 int mgqp_device_count(void) {

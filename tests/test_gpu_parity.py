@@ -414,6 +414,21 @@ def test_multi_device_entry_point(gpu, restatement):
     assert_bit_identical(r._asdict(), _oracle(restatement, b), f"multi{len(devs)}")
 
 
+def test_multi_device_entry_point_on_two_or_more_gpus(gpu, restatement):
+    """solve_quadprog_batched_multi across real devices: needs a multi-GPU lease (skipped, not passed, without one).
+    Every device must have taken chunks from the shared queue and the answers must be bit-identical."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    devs = list(range(torch.cuda.device_count()))
+    b = workloads.make("C5", 400003)
+    r = gpu.solve_quadprog_batched_multi(*b.fields(), devices=devs, want_active_set=True, chunk=8192)
+    chunks = gpu.last_multi_chunks()
+    assert len(chunks) == len(devs) and all(c > 0 for c in chunks) and sum(chunks) == -(-400003 // 8192)
+    ref = _oracle(restatement, b)
+    assert_bit_identical(r._asdict(), ref, f"multi{len(devs)}")
+
+
 def test_single_qp_reference_semantics(gpu, restatement):
     """solve_quadprog(G, g0, CE, ce0, CI, ci0, x): cost returned, G overwritten by its factor,
     +inf when infeasible, the reference's two exception types."""
