@@ -83,6 +83,12 @@ MGQP_HOST inline TileView make_tile_view(int n, int p, int m, int gw) {
 
 struct TileOut {   // global-memory outputs, already offset to the first QP of the tile
   double* x; double* f; int* status; int* iq; int* A; int* iters;
+  // solveNextStep's retry (src/mgqp.cpp:717-735) answered from THIS solve where that is exact: the second call
+  // runs without inequalities on the G the first call left behind, its Cholesky factor.  With G == I (the
+  // reference's own caller, :672) the factor is G itself, so the retry repeats this solve's equality phase
+  // operation for operation and returns the state right after it.  When set, a QP of an all-identity warp whose
+  // answer is NaN / +inf is reported as that state with MGQP_STATUS_RETRIED (= 16) instead.
+  bool fuse_retry = false;
 };
 
 // sqrt(a^2+b^2) exactly as QuadProg++'s `distance` (weak symbol in QuadProg++.o)
@@ -521,6 +527,11 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   }
   if (in_n) sx[li] = xv;
   wp_sync();
+  // the state a retry without inequalities would return (see TileOut::fuse_retry)
+  const bool fused = out.fuse_retry && all_identity;
+  const double x_eq = xv, f_eq = f;
+  const int iq_eq = iq, A_eq = Av;
+  const bool done_eq = done;
 
   // ------------------------------------------------------------------ active-set iteration
   const double thr = d_mul(d_mul(d_mul(d_mul((double)m, MGQP_EPS), c1), c2), 100.0);
@@ -734,6 +745,16 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   }
 
   // ------------------------------------------------------------------ results
+  if (fused && !done_eq && (f != f || f == d_inf()) && status != ST_NOT_PD && status != ST_EQ_DEPENDENT &&
+      f_eq == f_eq && d_abs(f_eq) < d_inf()) {
+    // (a retry whose own cost is NaN / inf is left to the generic pass: it zeroes the command)
+    xv = x_eq;
+    f = f_eq;
+    iq = iq_eq;
+    Av = A_eq;
+    steps = 0;
+    status = 16;  // MGQP_STATUS_RETRIED | ok
+  }
   if (g < cnt) {
     if (in_n) out.x[g * n + li] = xv;
     if (li == 0) {

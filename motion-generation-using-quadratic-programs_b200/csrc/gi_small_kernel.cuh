@@ -29,6 +29,7 @@ struct SmallParams {
   const unsigned char* ci_row;
   long long s_ci_val, s_ci_row;
   const unsigned long long* batch_dev;  // if set: the number of QPs lives on the device (<= batch)
+  int fuse_retry;        // TileOut::fuse_retry
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant_
     out.iq = P.iq ? P.iq + q0 : nullptr;
     out.A = P.A ? P.A + q0 * (P.tv.p + P.tv.m) : nullptr;
     out.iters = P.iters ? P.iters + q0 : nullptr;
+    out.fuse_retry = P.fuse_retry != 0;
     gi_solve_tile<GW, FMA>(P.tv, ws, cnt, P.max_iter, out);
 
     // generic-proxy accesses to the block are done; order them before the next async-proxy write

@@ -52,6 +52,9 @@ int fail(int rc, const char* fmt, ...) {
   } while (0)
 
 constexpr int kMaxDev = 16;
+// internal flag bit (never part of the ABI): the first solve of a retry call may answer the retry itself where
+// that is exact (gi_small.cuh, TileOut::fuse_retry)
+constexpr int kFlagFuseRetry = 1 << 30;
 // Work-queue heads, one slot per launch, reused round robin: two launches only ever share a slot if
 // more than kTicketRing launches of this library are in flight on one device at the same time.
 constexpr int kTicketRing = 4096;
@@ -470,6 +473,7 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const un
   P.bar_bytes = pl.bar_bytes;
   P.ticket = ticket;
   P.batch_dev = batch_dev;
+  P.fuse_retry = (d->flags & kFlagFuseRetry) ? 1 : 0;
   const int gi = pl.gw == 8 ? 0 : pl.gw == 16 ? 1 : 2;
   if (pl.gw == 8) return fast ? launch_small<8, true>(ctx, pl, P, st, gi, 1) : launch_small<8, false>(ctx, pl, P, st, gi, 0);
   if (pl.gw == 16) return fast ? launch_small<16, true>(ctx, pl, P, st, gi, 1) : launch_small<16, false>(ctx, pl, P, st, gi, 0);
@@ -489,9 +493,16 @@ struct AsyncBuf {
 // see retry.cuh.  Asynchronous like the plain call: the second launch reads the number of QPs that go
 // round again from device memory.
 int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
-  if (!d || !(d->flags & MGQP_FLAG_RETRY_WITHOUT_CI)) return solve_device_once(d, device, st);
+  if (!d) return solve_device_once(d, device, st);
+  if (!(d->flags & MGQP_FLAG_RETRY_WITHOUT_CI)) {
+    if (!(d->flags & kFlagFuseRetry)) return solve_device_once(d, device, st);
+    mgqp_batch plain = *d;  // the internal bit is not part of the ABI
+    plain.flags &= ~kFlagFuseRetry;
+    return solve_device_once(&plain, device, st);
+  }
   mgqp_batch first = *d;
   first.flags &= ~MGQP_FLAG_RETRY_WITHOUT_CI;
+  first.flags |= kFlagFuseRetry;
   int rc = solve_device_once(&first, device, st);
   if (rc || d->batch == 0) return rc;
   if (d->n > 1024) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "MGQP_FLAG_RETRY_WITHOUT_CI serves n <= 1024");
@@ -550,7 +561,7 @@ int solve_device(const mgqp_batch* d, int device, cudaStream_t st) {
   second.sG = n * n; second.sg0 = n; second.sCE = n * p; second.sce0 = p;
   second.x = x2; second.f = f2; second.status = st2; second.iq = iq2; second.A = p ? A2 : nullptr; second.iters = it2;
   second.max_iter = d->max_iter;
-  second.flags = first.flags;
+  second.flags = first.flags & ~kFlagFuseRetry;
   rc = solve_device_once(&second, device, st, count);
   if (!rc) {
     RetryScatter sc;
