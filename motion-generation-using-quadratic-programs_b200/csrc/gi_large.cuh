@@ -50,12 +50,16 @@ namespace mgqp {
 #ifndef MGQP_ELL_K
 #define MGQP_ELL_K 64
 #endif
+#ifndef MGQP_LARGE_PARHYP
+#define MGQP_LARGE_PARHYP 0
+#endif
 
 struct LargeView {
   int n, p, m, T;
   // shared memory, in doubles from the (16-byte aligned) base
   int ox, oz, od, onp, orr, ou, oxold, ouold, oh, occ, oss, oxny, ored, obc, orow;
-  int oredi, oA, oAold;   // ints, byte offsets
+  int onzv;               // doubles: values of the pending column's nonzeros (<= MGQP_ELL_K)
+  int oredi, oA, oAold, onzr;   // ints, byte offsets (onzr: rows of the pending column's nonzeros)
   int oact, oexcl, oskip; // bytes, byte offsets
   int smem_bytes;
   int ell_k;              // capacity of the ELL form of CI (nonzeros kept per column)
@@ -81,10 +85,12 @@ MGQP_HOST inline LargeView make_large_view(int n, int p, int m, int T) {
   v.ored = o; o += T;
   v.obc = o; o += 16;
   v.orow = o; o += 2 * MGQP_ROWBLK * n;  // double-buffered block of R / L rows for the serial solves
+  v.onzv = o; o += MGQP_ELL_K;
   int b = o * 8;
   v.oredi = b; b += 4 * T;
   v.oA = b; b += 4 * (n + 2);
   v.oAold = b; b += 4 * (n + 2);
+  v.onzr = b; b += 4 * MGQP_ELL_K;
   v.oact = b; b += m;
   v.oexcl = b; b += m;
   v.oskip = b; b += n + 1;
@@ -127,6 +133,8 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   double* sred = sm + v.ored;
   double* sbc = sm + v.obc;    // broadcast slots
   double* srow = sm + v.orow;  // 2 x MGQP_ROWBLK rows
+  double* snzv = sm + v.onzv;  // the pending inequality column in sparse form (values, rows): see direction()
+  int* snzr = reinterpret_cast<int*>(smem + v.onzr);
   int* sredi = reinterpret_cast<int*>(smem + v.oredi);
   int* A = reinterpret_cast<int*>(smem + v.oA);
   int* Aold = reinterpret_cast<int*>(smem + v.oAold);
@@ -446,14 +454,53 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     blk_sync();
   }
 
+  // Sparse form of d = J^T np.  d_i = sum_j J[j][i] np[j] is a sum that starts at +0.0; a term with np[j] == 0 is
+  // +-0.0 as long as J[j][i] is finite and can then not change a bit of it (a partial sum is never -0.0).  J is
+  // stored transposed, thread i walks ITS OWN row of that array: 32 different cache lines per load instruction,
+  // the one uncoalesced access pattern of this kernel -- with the few nonzeros of a bound / integrator column
+  // (ELL lists, ascending rows = the reference's order) it shrinks from n to nnz loads per thread.
+  // j_finite: no entry of J is inf / NaN (tracked wherever J is written; the tensor-core mode does not track).
+  int np_nnz = -1;        // >= 0: snzv / snzr hold the pending column's nonzeros
+  bool j_bad_mine = false;
+  bool j_finite = FMA || !fail;
+  if (!FMA && !fail && !dense_done) {
+    // J = L^-T as just built: finite iff every entry this thread owns is (rows i = tid, tid + T, ...)
+    bool bad = false;
+    MGQP_UNROLL1
+    for (int i = tid; i < n; i += T) {
+      MGQP_UNROLL4
+      for (int r = 0; r < n; r++) bad = bad || !(d_abs(J[(size_t)r * n + i]) < INF);
+    }
+    if (tid == 0) sredi[0] = 0;
+    blk_sync();
+    if (bad) sredi[0] = 1;
+    blk_sync();
+    j_finite = sredi[0] == 0;
+    blk_sync();
+  }
   // d = J^T np ; z = J[:, iq:] d[iq:] ; r = R[0:iq,0:iq]^-1 d[0:iq]
   auto direction = [&]() {
+#ifdef MGQP_LARGE_NO_SPARSE_D
+    if (false) {
+#else
+    if (np_nnz >= 0 && j_finite) {
+#endif
+      MGQP_UNROLL1
+      for (int i = tid; i < n; i += T) {
+        double s = 0.0;
+        const double* Ji = J + (size_t)i * n;
+        MGQP_UNROLL8
+        for (int k = 0; k < np_nnz; k++) s = mad<FMA>(Ji[snzr[k]], snzv[k], s);
+        sd[i] = s;
+      }
+    } else {
     MGQP_UNROLL1
     for (int i = tid; i < n; i += T) {
       double s = 0.0;
       MGQP_UNROLL16
       for (int j = 0; j < n; j++) s = mad<FMA>(J[(size_t)i * n + j], snp[j], s);  // J[j][i]
       sd[i] = s;
+    }
     }
     blk_sync();
     MGQP_UNROLL1
@@ -470,8 +517,50 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
 
   // add_constraint (Appendix A).  Returns the reference's bool; iq is incremented.
   auto add_constraint = [&]() -> bool {
-    // (1) serial chain: hypotenuses only.  sh[j] = h of rotation j, skip[j] = |h| < eps.
-    if (tid == 0) {
+    // (1) hypotenuses only.  sh[j] = h of rotation j, skip[j] = |h| < eps.
+    // Optional (-DMGQP_LARGE_PARHYP=1, tensor-core / FMA mode only): h_j = sqrt(sum_{k >= j-1} d[k]^2) as a running
+    // sum of squares and parallel square roots instead of one thread's chain of n dependent divisions and square
+    // roots.  +35 % on C4, but NOT enabled: the hypotenuses then differ from `distance`'s by an ulp or so, and on
+    // 1 of 592 horizon-stacked QPs (degenerate instances, where the algorithm's path decides the answer) the final
+    // active set differed from the reference's -- outside the north-star gate.
+    bool chain = true;
+#if MGQP_LARGE_PARHYP
+    if (FMA) {
+      bool wide = false;
+      MGQP_UNROLL1
+      for (int j = tid; j < n; j += T) {
+        const double a = d_abs(sd[j]);
+        wide = wide || !(a < 1e140) || (a != 0.0 && a < 1e-140);
+      }
+      if (tid == 0) sredi[2] = 0;
+      blk_sync();
+      if (wide) sredi[2] = 1;
+      blk_sync();
+      chain = sredi[2] != 0;
+      if (!chain) {
+        // S_j = d[j-1]^2 + S_{j+1} as ONE chain of fused multiply-adds (a few thousand cycles, against the chain of
+        // divisions and square roots it replaces), so that consecutive hypotenuses stay consistent to one rounding:
+        // c^2 + s^2 = (d[j-1]^2 + S_{j+1}) / S_j.  (Independent suffix sums per j drift by ~1e-14 per rotation, and
+        // tens of thousands of rotations then cost J its orthogonality: measured 1e-9 in x.)
+        if (tid == 0) {
+          double acc = (n > 0) ? d_mul(sd[n - 1], sd[n - 1]) : 0.0;
+          MGQP_UNROLL4
+          for (int j = n - 1; j >= iq + 1; j--) {
+            acc = d_fma(sd[j - 1], sd[j - 1], acc);
+            sh[j] = acc;
+          }
+        }
+        blk_sync();
+        MGQP_UNROLL1
+        for (int j = iq + 1 + tid; j <= n - 1; j += T) {
+          const double h = d_sqrt(sh[j]);
+          skip[j] = (d_abs(h) < MGQP_EPS) ? 1 : 0;
+          sh[j] = h;
+        }
+      }
+    }
+#endif
+    if (chain && tid == 0) {
       double carry = (n > 0) ? d_abs(sd[n - 1]) : 0.0;  // |current d[j]|
       MGQP_UNROLL1
       for (int j = n - 1; j >= iq + 1; j--) {
@@ -539,7 +628,9 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
           const double t1 = t1v[u];
           if (!skip[jj]) {
             const double n1 = d_add(d_mul(t1, scc[jj]), d_mul(t2, sss[jj]));
-            Jk[(size_t)jj * n] = d_sub(d_mul(sh[jj], d_add(t1, n1)), t2);
+            const double n2 = d_sub(d_mul(sh[jj], d_add(t1, n1)), t2);
+            Jk[(size_t)jj * n] = n2;
+            if (!FMA) j_bad_mine = j_bad_mine || !(d_abs(n1) < INF) || !(d_abs(n2) < INF);
             t2 = n1;
           } else {
             Jk[(size_t)jj * n] = t2;
@@ -552,7 +643,9 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
         const double t1 = Jk[(size_t)(j - 1) * n];
         if (!skip[j]) {
           const double n1 = d_add(d_mul(t1, scc[j]), d_mul(t2, sss[j]));
-          Jk[(size_t)j * n] = d_sub(d_mul(sh[j], d_add(t1, n1)), t2);
+          const double n2 = d_sub(d_mul(sh[j], d_add(t1, n1)), t2);
+          Jk[(size_t)j * n] = n2;
+          if (!FMA) j_bad_mine = j_bad_mine || !(d_abs(n1) < INF) || !(d_abs(n2) < INF);
           t2 = n1;
         } else {
           Jk[(size_t)j * n] = t2;
@@ -560,6 +653,13 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
         }
       }
       if (iq + 1 <= n - 1) Jk[(size_t)iq * n] = t2;
+    }
+    if (!FMA && j_finite) {  // (uniform: j_finite is a CTA-wide value)
+      if (tid == 0) sredi[1] = 0;
+      blk_sync();
+      if (j_bad_mine) sredi[1] = 1;
+      blk_sync();
+      j_finite = sredi[1] == 0;
     }
     // column iq of R <- d[0..iq]
     MGQP_UNROLL1
@@ -648,11 +748,20 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
           double* Jk = J + k;
           const double t1 = Jk[(size_t)j * n], t2 = Jk[(size_t)(j + 1) * n];
           const double n1 = d_add(d_mul(t1, cc), d_mul(t2, ss));
+          const double n2 = d_sub(d_mul(xny, d_add(n1, t1)), t2);
           Jk[(size_t)j * n] = n1;
-          Jk[(size_t)(j + 1) * n] = d_sub(d_mul(xny, d_add(n1, t1)), t2);
+          Jk[(size_t)(j + 1) * n] = n2;
+          if (!FMA) j_bad_mine = j_bad_mine || !(d_abs(n1) < INF) || !(d_abs(n2) < INF);
         }
       }
       blk_sync();
+    }
+    if (!FMA && j_finite) {
+      if (tid == 0) sredi[1] = 0;
+      blk_sync();
+      if (j_bad_mine) sredi[1] = 1;
+      blk_sync();
+      j_finite = sredi[1] == 0;
     }
   };
 
@@ -669,6 +778,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   for (int e = 0; e < p && !done; e++) {
     MGQP_UNROLL1
     for (int j = tid; j < n; j += T) snp[j] = MGQP_LDG(io.CE + (size_t)j * p + e);
+    np_nnz = -1;
     blk_sync();
     direction();
     dot0(sz, sz, 0);
@@ -882,6 +992,15 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
         } else {
           MGQP_UNROLL1
           for (int j = tid; j < n; j += T) snp[j] = MGQP_LDG(io.CI + (size_t)j * m + ip);
+          np_nnz = -1;
+          if (any_sparse && ell_nnz[ip] != ELL_DENSE) {
+            np_nnz = (int)ell_nnz[ip];
+            MGQP_UNROLL1
+            for (int k = tid; k < np_nnz; k += T) {
+              snzv[k] = ell_val[(size_t)k * m + ip];
+              snzr[k] = (int)ell_row[(size_t)k * m + ip];
+            }
+          }
           if (tid == 0) {
             su[iq] = 0.0;
             A[iq] = ip;

@@ -109,8 +109,10 @@ int device_ctx(int device, DeviceCtx** out) {
     CU(cudaDeviceGetAttribute(&c.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     {
       // stream-ordered workspaces (CTA-per-QP kernel, retry pass) are allocated per call from a pool of the
-      // library's own: freed blocks stay cached there (up to 1 GB; more goes back to the driver at the next
-      // synchronisation) instead of being parked in the device's default pool, which the application uses
+      // library's own: freed blocks stay cached there (up to 6 GB -- the CTA-per-QP kernel's workspace for the
+      // horizon-stacked shape is 1.3 GB, a cascade chunk 1.5 GB; handing those back to the driver at every
+      // synchronisation made consecutive calls vary by 4x -- more goes back at the next synchronisation) instead of
+      // being parked in the device's default pool, which the application uses
       cudaMemPoolProps props;
       memset(&props, 0, sizeof props);
       props.allocType = cudaMemAllocationTypePinned;
@@ -118,7 +120,7 @@ int device_ctx(int device, DeviceCtx** out) {
       props.location.type = cudaMemLocationTypeDevice;
       props.location.id = device;
       CU(cudaMemPoolCreate(&c.pool, &props));
-      unsigned long long keep = 1ull << 30;
+      unsigned long long keep = 6ull << 30;
       cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     CU(cudaMalloc(&c.tickets, kTicketRing * sizeof(unsigned)));
@@ -300,6 +302,10 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
   if (const char* e = std::getenv("MGQP_LARGE_CTAS_PER_SM")) cap_sm = std::atoi(e);  // tuning knob
   if (per_sm > cap_sm) per_sm = cap_sm;
   long long ctas = (long long)ctx->sms * per_sm;
+  if (const char* e = std::getenv("MGQP_LARGE_MAX_CTAS")) {  // tuning knob: fewer CTAs in flight (L2 residency)
+    const long long c = std::atoll(e);
+    if (c >= 1 && c < ctas) ctas = c;
+  }
   if (ctas > P.batch) ctas = P.batch;
   const long long ws_bytes = lp.v.ws_doubles * 8;
   const long long cap = (8ll << 30) / ws_bytes;  // keep the workspace under 8 GB

@@ -1,0 +1,16 @@
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mpc or beyond or shapes or retry" 2>&1 | tail -3
+python - <<'P'
+import sys, time, os; sys.path.insert(0,'.')
+import numpy as np, torch, mgqp_b200
+from mgqp_b200 import workloads
+dev=torch.device('cuda:0')
+t=workloads.make_c4_device(2368, dev)
+for T in ('256','512'):
+  os.environ['MGQP_LARGE_T']=T
+  for fl in (0,1):
+    for rep in range(2):
+        torch.cuda.synchronize(); t0=time.time()
+        out=mgqp_b200.solve_quadprog_batched(*t, flags=fl); torch.cuda.synchronize()
+        dt=time.time()-t0
+    print('T',T,'flags',fl,'C4 2368: %.1f ms -> %.4g QP/s'%(dt*1e3, 2368/dt))
+P
