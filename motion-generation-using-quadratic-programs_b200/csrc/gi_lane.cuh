@@ -79,6 +79,9 @@
 #ifndef MGQP_LANE_K
 #define MGQP_LANE_K 1
 #endif
+#ifndef MGQP_LANE_UNROLLED_SETUP
+#define MGQP_LANE_UNROLLED_SETUP 1
+#endif
 
 namespace mgqp {
 
@@ -168,6 +171,9 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
   g.xny = d_div(ss, d_add(1.0, cc));
   return g;
 }
+
+// a / b out of line: the unrolled set-up has 63 divisions, inlined they are 16 instructions each plus a slow path
+MGQP_DEV_NOINLINE double ln_div(double a, double b) { return d_div(a, b); }
 
 struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
@@ -514,6 +520,90 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
   bool fail = false;
   bool lfin = true;  // every off-diagonal entry of the Cholesky factor is finite
   double bad_pivot = 0.0;
+  double c2 = 0.0;
+  bool setup_done = false;
+#if MGQP_LANE_UNROLLED_SETUP
+  {
+    // Fast path: the whole set-up unrolled over the compile-time N, in registers, touching only the entries the
+    // reference's loops produce something from (56 + 56 + 42 multiply-subtracts at N = 7 instead of the 147 + 147
+    // of the row-parallel rolled form below, no loop control, no address arithmetic), divisions out of line.  Same
+    // operations in the same order per element.  It leaves the slot untouched until it knows it can finish: a
+    // factor with inf / NaN in it (a poisoned G) goes to the rolled form, whose full loops spread the poison
+    // exactly as the reference does.
+    double L[N][N];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+      for (int j = i; j < N; j++) {
+        double sum = Ls[i * N + j];
+#pragma unroll
+        for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, L[i][k], L[j][k]);
+        if (j == i) {
+          if (!bad && sum <= 0.0) {
+            bad = true;
+            bad_pivot = sum;
+          }
+          L[i][i] = d_sqrt(sum);
+          lfin = lfin && (L[i][i] < INF);
+        } else {
+          L[j][i] = ln_div(sum, L[i][i]);
+          lfin = lfin && (d_abs(L[j][i]) < INF);
+        }
+      }
+    }
+    if (bad) {
+      fail = true;
+      setup_done = true;
+    } else if (lfin) {
+      setup_done = true;
+      // J = L^-T, row i = forward_elimination(L, e_i); entries left of the diagonal are exactly +0.0 (finite factor)
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double Ji[N];
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+          if (r < i) {
+            Ji[r] = 0.0;
+          } else {
+            double acc = (r == i) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = i; j < r; j++) acc = msub<FMA>(acc, L[r][j], Ji[j]);
+            Ji[r] = ln_div(acc, L[r][r]);
+          }
+          Js[i * N + r] = Ji[r];
+        }
+        c2 = d_add(c2, Ji[i]);
+      }
+      // x = -G^-1 g0: forward then backward elimination
+      double y[N], xb[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        double a = g0r[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) a = msub<FMA>(a, L[i][j], y[j]);
+        y[i] = ln_div(a, L[i][i]);
+      }
+#pragma unroll
+      for (int i = N - 1; i >= 0; i--) {
+        double a = y[i];
+#pragma unroll
+        for (int j = i + 1; j < N; j++) a = msub<FMA>(a, L[j][i], xb[j]);
+        xb[i] = ln_div(a, L[i][i]);
+      }
+      double fs = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        x[i] = -xb[i];
+        fs = mad<FMA>(g0r[i], x[i], fs);
+      }
+      f = d_mul(0.5, fs);
+    } else {
+      lfin = true;  // the rolled form below starts over
+    }
+  }
+#endif
+  if (!setup_done) {
 #pragma unroll 1
   for (int i = 0; i < N && !fail; i++) {
     double sum[N];
@@ -549,11 +639,11 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
     }
   }
 
-  double c2 = 0.0;
+  }  // rolled Cholesky
   if (fail) {
     status = 2;
     f = bad_pivot;
-  } else {
+  } else if (!setup_done) {
     // J = L^-T: all N rows (row i = forward_elimination(L, e_i)) advance together, column by column
 #pragma unroll 1
     for (int r = 0; r < N; r++) {
