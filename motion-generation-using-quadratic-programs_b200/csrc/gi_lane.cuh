@@ -79,6 +79,18 @@
 #ifndef MGQP_LANE_K
 #define MGQP_LANE_K 1
 #endif
+#ifndef MGQP_LANE_SWEEP_GROUP
+#define MGQP_LANE_SWEEP_GROUP 3
+#endif
+#ifndef MGQP_LANE_GIVENS_SPLIT
+#define MGQP_LANE_GIVENS_SPLIT 1
+#endif
+#ifndef MGQP_LANE_SPLIT_SWEEP
+#define MGQP_LANE_SPLIT_SWEEP 0
+#endif
+#ifndef MGQP_LANE_DIV_GROUPS
+#define MGQP_LANE_DIV_GROUPS 1
+#endif
 #ifndef MGQP_LANE_UNROLLED_SETUP
 #define MGQP_LANE_UNROLLED_SETUP 1
 #endif
@@ -146,6 +158,8 @@ MGQP_DEV double ln_distance(double a, double b) {
   return d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t))));
 }
 
+MGQP_DEV_NOINLINE double ln_distance_ni(double a, double b) { return ln_distance(a, b); }
+
 // (c, s) -> normalised rotation coefficients exactly as add_constraint / delete_constraint derive
 // them (Appendix A).  One shared, non-inlined copy: it holds four IEEE divisions and a square root,
 // and the unrolled sweeps call it from twelve places.  valid == 0 <=> the reference `continue`s.
@@ -155,6 +169,39 @@ struct LaneGivens {
 };
 MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
   LaneGivens g;
+#if MGQP_LANE_GIVENS_SPLIT
+  // The four divisions on the split inline path of the division (warp_prims.cuh): no branch between them, c and s
+  // share the refinement of 1 / h, and one test at the end sends the whole call to the form below when any of the
+  // quotients needs the division's general routine (exact zeros in d, operands at the ends of the exponent range).
+  {
+    bool ok = true;
+    const double a1 = d_abs(cc), b1 = d_abs(ss);
+    const bool agt = a1 > b1;
+    const bool differ = agt || (b1 > a1);
+    const double hi = differ ? (agt ? a1 : b1) : 1.0, lo = differ ? (agt ? b1 : a1) : 1.0;
+    const double t = d_div_rcp(lo, hi, d_rcp_refined(hi), ok);
+    const double h = differ ? d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t)))) : d_mul(a1, d_sqrt(2.0));
+    const double rh = d_rcp_refined(h);
+    double s1 = d_div_rcp(ss, h, rh, ok);
+    double c1 = d_div_rcp(cc, h, rh, ok);
+    double dg = h;
+    if (c1 < 0.0) {
+      c1 = -c1;
+      s1 = -s1;
+      dg = -h;
+    }
+    const double den = d_add(1.0, c1);
+    const double xq = d_div_rcp(d_abs(s1), den, d_rcp_refined(den), ok);  // s / den == -((-s) / den) exactly
+    if (ok) {
+      g.valid = !(d_abs(h) < MGQP_EPS);
+      g.c = c1;
+      g.s = s1;
+      g.diag = dg;
+      g.xny = d_signbit(s1) ? -xq : xq;
+      return g;
+    }
+  }
+#endif
   const double h = ln_distance(cc, ss);
   g.valid = !(d_abs(h) < MGQP_EPS);
   ss = d_div(ss, h);
@@ -174,6 +221,58 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
 
 // a / b out of line: the unrolled set-up has 63 divisions, inlined they are 16 instructions each plus a slow path
 MGQP_DEV_NOINLINE double ln_div(double a, double b) { return d_div(a, b); }
+// ... and two / three quotients over one divisor per call: independent chains that overlap (the results come back
+// in registers)
+struct LnD2 { double a, b; };
+struct LnD3 { double a, b, c; };
+MGQP_DEV_NOINLINE LnD2 ln_div2(double a0, double a1, double b) {
+  LnD2 r;
+  r.a = d_div(a0, b);
+  r.b = d_div(a1, b);
+  return r;
+}
+MGQP_DEV_NOINLINE LnD3 ln_div3(double a0, double a1, double a2, double b) {
+  LnD3 r;
+  r.a = d_div(a0, b);
+  r.b = d_div(a1, b);
+  r.c = d_div(a2, b);
+  return r;
+}
+// q[0..cnt) /= b in groups of three and two (cnt is a constant once the caller's loop is unrolled)
+template <int K>
+MGQP_DEV void ln_div_all(double (&q)[K], int cnt, double b) {
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    // group starts: 3-groups while more than four remain or exactly three, then 2-groups, then a single
+    int at = 0;
+    bool start = false;
+    int len = 0;
+    while (at <= k && at < cnt) {
+      const int left = cnt - at;
+      len = (left >= 3 && left != 4) ? 3 : (left >= 2 ? 2 : 1);
+#if !MGQP_LANE_DIV_GROUPS
+      len = 1;
+#endif
+      if (at == k) { start = true; break; }
+      at += len;
+    }
+    if (start) {
+      if (len == 3) {
+        if (k + 2 < K) {
+          const LnD3 r = ln_div3(q[k], q[k + 1], q[k + 2], b);
+          q[k] = r.a; q[k + 1] = r.b; q[k + 2] = r.c;
+        }
+      } else if (len == 2) {
+        if (k + 1 < K) {
+          const LnD2 r = ln_div2(q[k], q[k + 1], b);
+          q[k] = r.a; q[k + 1] = r.b;
+        }
+      } else {
+        q[k] = ln_div(q[k], b);
+      }
+    }
+  }
+}
 
 struct LaneIO {  // global memory, this lane's QP
   const double* G; const double* g0; const double* CE; const double* ce0; const double* CI; const double* ci0;
@@ -534,20 +633,28 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
     bool bad = false;
 #pragma unroll
     for (int i = 0; i < N; i++) {
+      double col[N];  // [0]: the pivot; [j - i]: the numerators of L[j][i]
 #pragma unroll
       for (int j = i; j < N; j++) {
         double sum = Ls[i * N + j];
 #pragma unroll
         for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, L[i][k], L[j][k]);
-        if (j == i) {
-          if (!bad && sum <= 0.0) {
-            bad = true;
-            bad_pivot = sum;
-          }
-          L[i][i] = d_sqrt(sum);
-          lfin = lfin && (L[i][i] < INF);
-        } else {
-          L[j][i] = ln_div(sum, L[i][i]);
+        col[j - i] = sum;
+      }
+      if (!bad && col[0] <= 0.0) {
+        bad = true;
+        bad_pivot = col[0];
+      }
+      L[i][i] = d_sqrt(col[0]);
+      lfin = lfin && (L[i][i] < INF);
+      {
+        double q[N];
+#pragma unroll
+        for (int j = i + 1; j < N; j++) q[j - i - 1] = col[j - i];
+        ln_div_all<N>(q, N - 1 - i, L[i][i]);
+#pragma unroll
+        for (int j = i + 1; j < N; j++) {
+          L[j][i] = q[j - i - 1];
           lfin = lfin && (d_abs(L[j][i]) < INF);
         }
       }
@@ -557,24 +664,28 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
       setup_done = true;
     } else if (lfin) {
       setup_done = true;
-      // J = L^-T, row i = forward_elimination(L, e_i); entries left of the diagonal are exactly +0.0 (finite factor)
+      // J = L^-T, row i = forward_elimination(L, e_i); entries left of the diagonal are exactly +0.0 (finite
+      // factor).  Column by column: the r + 1 entries of column r share the divisor L[r][r].
+      double Jv[N][N];
 #pragma unroll
-      for (int i = 0; i < N; i++) {
-        double Ji[N];
+      for (int r = 0; r < N; r++) {
+        double q[N];
 #pragma unroll
-        for (int r = 0; r < N; r++) {
-          if (r < i) {
-            Ji[r] = 0.0;
-          } else {
-            double acc = (r == i) ? 1.0 : 0.0;
+        for (int i = 0; i <= r; i++) {
+          double acc = (r == i) ? 1.0 : 0.0;
 #pragma unroll
-            for (int j = i; j < r; j++) acc = msub<FMA>(acc, L[r][j], Ji[j]);
-            Ji[r] = ln_div(acc, L[r][r]);
-          }
-          Js[i * N + r] = Ji[r];
+          for (int j = i; j < r; j++) acc = msub<FMA>(acc, L[r][j], Jv[i][j]);
+          q[i] = acc;
         }
-        c2 = d_add(c2, Ji[i]);
+        ln_div_all<N>(q, r + 1, L[r][r]);
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          if (i <= r) Jv[i][r] = q[i];
+          Js[i * N + r] = (i <= r) ? q[i] : 0.0;
+        }
       }
+#pragma unroll
+      for (int i = 0; i < N; i++) c2 = d_add(c2, Jv[i][i]);
       // x = -G^-1 g0: forward then backward elimination
       double y[N], xb[N];
 #pragma unroll
@@ -993,6 +1104,131 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
       bool degenerate = false;
       if (do_add) {
 #pragma unroll
+#if MGQP_LANE_SPLIT_SWEEP
+        // The sweep's rotations j = N-1 .. iq+1 chain through ONE number only: rotation j-1 starts from
+        // distance(d[j-2], |diag_j|).  Pass 1 runs that chain (one division and one square root per rotation);
+        // the three remaining divisions of every rotation (c, s, s / (1 + c)) do not feed it, and pass 2 computes
+        // them for a few rotations side by side on the split inline path of the division (warp_prims.cuh) --
+        // out of a call per rotation with four divisions in a row they were a tenth of the kernel's time
+        // (profiles/r02_notes.md).  Same operations on the same operands: a quotient's sign is separated from its
+        // magnitude where the numerator's sign is only known later (x / h == -((-x) / h) exactly).
+        // [j]: the rotation's hypotenuse, its second operand (sign pending if it is a diag) -- parked in the slot's d
+        // and r vectors (dead until the sweep's result is stored there): the registers are all taken by J
+        double* gh = sr;
+        double* gb = sd;
+        bool gact[N], gdg[N];   // [j]: rotation happens; its second operand is the previous rotation's diag
+        {
+          double cur = dd[N - 1];
+          bool cur_dg = false;
+#pragma unroll
+          for (int j = N - 1; j >= 1; j--) {
+            gact[j] = false;
+            gh[j] = 1.0;
+            gb[j] = cur;
+            gdg[j] = cur_dg;
+            if (j >= iq + 1) {
+              const double h = ln_distance_ni(dd[j - 1], cur);
+              gh[j] = h;
+              if (!(d_abs(h) < MGQP_EPS)) {
+                gact[j] = true;
+                cur = h;
+                cur_dg = true;
+              } else {  // the reference `continue`s: d[j-1] stays what it was
+                cur = dd[j - 1];
+                cur_dg = false;
+              }
+            }
+          }
+        }
+        constexpr int GR = MGQP_LANE_SWEEP_GROUP;  // rotations whose divisions run side by side
+        bool prev_neg = false;  // the previous rotation's diag is -h
+#pragma unroll
+        for (int j0 = N - 1; j0 >= 1; j0 -= GR) {
+          if (j0 >= iq + 1) {
+            double gc[GR], gs[GR], gx[GR], gd[GR];
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < GR; u++) {
+              const int j = j0 - u;
+              if (j >= 1) {
+                const bool on = gact[j];
+                const double hn = on ? gh[j] : 1.0;
+                const double r = d_rcp_refined(hn);
+                gc[u] = d_div_rcp(on ? dd[j - 1] : 1.0, hn, r, ok);
+                gs[u] = d_div_rcp(on ? d_abs(gb[j]) : 1.0, hn, r, ok);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < GR; u++) {
+              const int j = j0 - u;
+              if (j >= 1) {
+                const bool bneg = gdg[j] ? prev_neg : d_signbit(gb[j]);
+                if (bneg) gs[u] = -gs[u];
+                const bool flip = gc[u] < 0.0;
+                if (flip) {
+                  gc[u] = -gc[u];
+                  gs[u] = -gs[u];
+                }
+                gd[u] = flip ? -gh[j] : gh[j];
+                if (gact[j]) prev_neg = flip;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < GR; u++) {
+              const int j = j0 - u;
+              if (j >= 1) {
+                const bool on = gact[j];
+                const double den = on ? d_add(1.0, gc[u]) : 1.0;
+                const double q = d_div_rcp(on ? d_abs(gs[u]) : 1.0, den, d_rcp_refined(den), ok);
+                gx[u] = d_signbit(gs[u]) ? -q : q;
+              }
+            }
+            if (ok) {
+#pragma unroll
+              for (int u = 0; u < GR; u++) {
+                const int j = j0 - u;
+                if (j >= 1) {
+                  if (gact[j]) {
+                    dd[j] = 0.0;
+                    dd[j - 1] = gd[u];
+#pragma unroll
+                    for (int k = 0; k < N; k++) {
+                      const double t1 = Jr[k][j - 1], t2 = Jr[k][j];
+                      const double n1 = d_add(d_mul(t1, gc[u]), d_mul(t2, gs[u]));
+                      Jr[k][j - 1] = n1;
+                      Jr[k][j] = d_sub(d_mul(gx[u], d_add(t1, n1)), t2);
+                    }
+                  }
+                }
+              }
+            } else {
+              // some quotient of the group needs the division's general routine (an exact zero in d, as sparse
+              // problems have them; a tiny or huge operand): the rotations one by one, as the reference orders them
+#pragma unroll
+              for (int u = 0; u < GR; u++) {
+                const int j = j0 - u;
+                if (j >= 1) {
+                  if (j >= iq + 1) {
+                    const LaneGivens g = ln_givens(dd[j - 1], dd[j]);
+                    if (g.valid) {
+                      dd[j] = 0.0;
+                      dd[j - 1] = g.diag;
+#pragma unroll
+                      for (int k = 0; k < N; k++) {
+                        const double t1 = Jr[k][j - 1], t2 = Jr[k][j];
+                        const double n1 = d_add(d_mul(t1, g.c), d_mul(t2, g.s));
+                        Jr[k][j - 1] = n1;
+                        Jr[k][j] = d_sub(d_mul(g.xny, d_add(t1, n1)), t2);
+                      }
+                      prev_neg = g.diag < 0.0;
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+#else
         for (int j = N - 1; j >= 1; j--) {
           if (j >= iq + 1) {
             const LaneGivens g = ln_givens(dd[j - 1], dd[j]);
@@ -1009,6 +1245,7 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
             }
           }
         }
+#endif
 #pragma unroll
         for (int i = 0; i < N; i++) sd[i] = dd[i];
         iq++;

@@ -10,6 +10,9 @@
 #ifndef MGQP_LANE_CTA_SYNC
 #define MGQP_LANE_CTA_SYNC 4
 #endif
+#ifndef MGQP_LANE_SYNC_ROUNDS
+#define MGQP_LANE_SYNC_ROUNDS 1
+#endif
 
 namespace mgqp {
 
@@ -111,14 +114,15 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
   // all stall samples were instruction-fetch misses.  The group's leader draws the tickets one round ahead, so
   // that every warp knows its next tile while it works on the current one.
   constexpr int GW = MGQP_LANE_CTA_SYNC;          // warps per group
+  constexpr int SR = MGQP_LANE_SYNC_ROUNDS;       // tiles per warp between two barriers
   __shared__ unsigned s_round_base[8];
   const int grp = warp / GW, wig = warp - grp * GW;
   const int grp_warps = (warps_per_cta - grp * GW) < GW ? (warps_per_cta - grp * GW) : GW;
   auto grp_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(grp_warps * 32) : "memory"); };
   auto draw = [&](long long round) {
     if (wig == 0 && lane == 0)
-      s_round_base[grp] = P.ticket ? atomicAdd(P.ticket, (unsigned)grp_warps)
-                                   : (unsigned)((round * gridDim.x + blockIdx.x) * warps_per_cta + grp * GW);
+      s_round_base[grp] = P.ticket ? atomicAdd(P.ticket, (unsigned)(SR * grp_warps))
+                                   : (unsigned)(((round * gridDim.x + blockIdx.x) * warps_per_cta + grp * GW) * SR);
   };
   grp_sync();
   draw(0);
@@ -129,7 +133,12 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
     draw(round + 1);
     grp_sync();
     const long long nxt = (long long)s_round_base[grp];
-    if (cur + wig < tiles) do_tile(cur + wig, nxt + wig);
+#pragma unroll 1
+    for (int sub = 0; sub < SR; sub++) {  // SR tiles per warp between two barriers
+      const long long tile = cur + sub * grp_warps + wig;
+      const long long tile_next = (sub + 1 < SR) ? tile + grp_warps : nxt + wig;
+      if (tile < tiles) do_tile(tile, tile_next);
+    }
     cur = nxt;
   }
 #else

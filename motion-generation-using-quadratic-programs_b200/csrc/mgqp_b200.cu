@@ -1122,6 +1122,71 @@ int mgqp_last_multi_chunks(int64_t* counts, int max_devices) {
   return n;
 }
 
+namespace mgqp {
+__global__ void div_check_kernel(long long count, unsigned long long seed, unsigned long long* out) {
+  unsigned long long acc = 0, bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    auto mix = [](unsigned long long z) {
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      return z ^ (z >> 31);
+    };
+    const unsigned long long ra = mix(seed + 2 * (unsigned long long)i * 0x9e3779b97f4a7c15ull);
+    const unsigned long long rb = mix(seed + (2 * (unsigned long long)i + 1) * 0x9e3779b97f4a7c15ull);
+    double a, b;
+    const int mode = (int)(i % 3);
+    if (mode == 0) {  // raw bit patterns: every exponent, denormals, inf, NaN
+      a = __longlong_as_double((long long)ra);
+      b = __longlong_as_double((long long)rb);
+    } else {          // exponents within 2^+-40 of one (mode 1) / of each other anywhere in the range (mode 2)
+      const unsigned long long ea = 1023ull - 40 + (ra >> 12) % 81, eb = 1023ull - 40 + (rb >> 12) % 81;
+      const unsigned long long sh = (mode == 2) ? (mix(ra ^ rb) % 1800) : 0;
+      const unsigned long long xa = (mode == 2) ? (ea + sh > 983 ? ea + sh - 983 : 1) : ea;
+      const unsigned long long xb = (mode == 2) ? (eb + sh > 983 ? eb + sh - 983 : 1) : eb;
+      a = __longlong_as_double((long long)((ra & 0x800fffffffffffffull) | ((xa & 0x7ff) << 52)));
+      b = __longlong_as_double((long long)((rb & 0x800fffffffffffffull) | ((xb & 0x7ff) << 52)));
+    }
+    bool ok = true;
+    const double r = d_rcp_refined(b);
+    const double q = d_div_rcp(a, b, r, ok);
+    const double a2 = __longlong_as_double((long long)mix(ra));  // a second numerator over the same refinement
+    bool ok2 = true;
+    const double q2 = d_div_rcp(a2, b, r, ok2);
+    if (ok) {
+      acc++;
+      if (__double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a, b))) bad++;
+    }
+    if (ok2) {
+      acc++;
+      if (__double_as_longlong(q2) != __double_as_longlong(__ddiv_rn(a2, b))) bad++;
+    }
+  }
+  atomicAdd(out, acc);
+  atomicAdd(out + 1, bad);
+}
+}  // namespace mgqp
+
+int mgqp_debug_div_check(int64_t count, uint64_t seed, int64_t* accepted, int64_t* mismatches) {
+  unsigned long long* d = nullptr;
+  unsigned long long h[2] = {0, 0};
+  cudaError_t e = cudaMalloc(&d, sizeof(h));
+  if (e == cudaSuccess) e = cudaMemset(d, 0, sizeof(h));
+  if (e == cudaSuccess) {
+    mgqp::div_check_kernel<<<1184, 256>>>((long long)count, (unsigned long long)seed, d);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  if (d) cudaFree(d);
+  if (e != cudaSuccess) {
+    g_last_error = std::string("mgqp_debug_div_check: ") + cudaGetErrorString(e);
+    return MGQP_ERR_CUDA;
+  }
+  if (accepted) *accepted = (int64_t)h[0];
+  if (mismatches) *mismatches = (int64_t)h[1];
+  return MGQP_OK;
+}
+
 int mgqp_device_count(void) {
   int c = 0;
   if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;

@@ -192,8 +192,19 @@ MGQP_DEV double d_add(double a, double b) { return a + b; }
 MGQP_DEV double d_sub(double a, double b) { return a - b; }
 MGQP_DEV double d_div(double a, double b) { return a / b; }
 MGQP_DEV double d_div_z(double a, double b) { return a / b; }
+// the split inline path of the device's division (warp_prims.cuh): here the quotient is the host's IEEE division and
+// `ok` follows the device's range tests, so that the callers' fallbacks are exercised on the CPU as well
+MGQP_DEV double d_rcp_refined(double) { return 0.0; }
+MGQP_DEV double d_div_rcp(double a, double b, double, bool& ok) {
+  const double q = a / b;
+  auto hi = [](double v) { unsigned long long u; memcpy(&u, &v, 8); return (unsigned)(u >> 32) & 0x7fffffffu; };
+  ok = ok && hi(q) > 0x00100000u && hi(q) <= 0x7f800000u && hi(b) < 0x7f800000u && hi(a) >= 0x03600000u &&
+       hi(a) <= 0x7f800000u;
+  return q;
+}
 MGQP_DEV double d_sqrt(double a) { return sqrt(a); }
 MGQP_DEV double d_fma(double a, double b, double c) { return fma(a, b, c); }
+MGQP_DEV bool d_signbit(double a) { return __builtin_signbit(a) != 0; }
 MGQP_DEV double d_abs(double a) { return fabs(a); }
 MGQP_DEV void d_acc_neg(double& acc, double a) { if (a < 0.0) acc = acc + a; }
 MGQP_DEV void d_or_if_nonzero(unsigned& mask, double a, unsigned bit) { if (a != 0.0) mask |= bit; }

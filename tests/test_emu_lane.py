@@ -155,3 +155,28 @@ def test_scan_ties_keep_the_first_index(emu_lib, restatement):
         b.ci0[:, dst] = b.ci0[:, src]
     b.ci0[:, [5, 20, 33, 1, 2]] -= 1.5      # make the duplicated bounds bite
     assert_bit_identical(lane_solve(emu_lib, b), _oracle(restatement, b), "ties")
+
+
+def test_sparse_direction_takes_the_sweeps_fallback(emu_lib, restatement):
+    """G = I with bound constraints: d = J' n has exact zeros, which the split division of the add_constraint sweep
+    hands back to the general routine (the emulator applies the device's range tests): both paths, same bits."""
+    rng = np.random.default_rng(77)
+    B, n, m = 3001, 7, 14
+    G = np.broadcast_to(np.eye(n), (B, n, n)).copy()
+    G[::3] *= rng.uniform(0.5, 2.0, (len(G[::3]), 1, 1))
+    g0 = rng.standard_normal((B, n)) * 3
+    CE = np.zeros((B, n, 1)); CE[:, 2, 0] = 1.0
+    CE[::5, 4, 0] = -0.5
+    ce0 = rng.standard_normal((B, 1)) * 0.1
+    CI = np.zeros((B, n, m))
+    CI[:, np.arange(n), np.arange(n)] = 1.0
+    CI[:, np.arange(n), n + np.arange(n)] = -1.0
+    ci0 = np.abs(rng.standard_normal((B, m))) * 0.7 + 0.2
+    b = workloads.QPBatch("sparse7", n, 1, m, G, g0, CE, ce0, CI, ci0)
+    ref = _oracle(restatement, b)
+    assert ref["iters"].mean() > 2
+    assert_bit_identical(lane_solve(emu_lib, b), ref, "sparse7")
+    # tiny and huge scales: operands outside the inline path's range
+    for scale in (1e-160, 1e150):
+        b2 = workloads.QPBatch("scaled", n, 1, m, G, g0 * scale, CE, ce0 * scale, CI, ci0 * scale)
+        assert_bit_identical(lane_solve(emu_lib, b2), _oracle(restatement, b2), f"scaled{scale}")

@@ -451,6 +451,38 @@ def test_single_qp_reference_semantics(gpu, restatement):
                 assert np.array_equal(G, z["G_factor"])
 
 
+def test_split_division_matches_the_compilers_division(gpu):
+    """The lane kernel's add_constraint sweep divides on the branch-free inline path of div.rn.f64
+    (csrc/warp_prims.cuh); wherever that path accepts a pair its quotient must be the compiler's, bit for bit."""
+    import ctypes as C
+    from mgqp_b200 import _api
+    L = _api.lib()
+    L.mgqp_debug_div_check.restype = C.c_int
+    L.mgqp_debug_div_check.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    for seed in (1, 0xC0FFEE):
+        acc, bad = C.c_int64(-1), C.c_int64(-1)
+        assert L.mgqp_debug_div_check(300_000_000, seed, C.byref(acc), C.byref(bad)) == 0
+        assert bad.value == 0
+        assert acc.value > 300_000_000      # two thirds of the draws are in the accepted range, two quotients each
+
+
+def test_sparse_direction_takes_the_sweeps_fallback(gpu, restatement):
+    """G = I with bound constraints: d = J' n has exact zeros, which the split division hands back to the general
+    routine; the sweep's one-by-one fallback must give the reference's bits."""
+    rng = np.random.default_rng(77)
+    B, n, m = 5003, 7, 14
+    G = np.broadcast_to(np.eye(n), (B, n, n)).copy()
+    g0 = rng.standard_normal((B, n)) * 3
+    CE = np.zeros((B, n, 1)); CE[:, 2, 0] = 1.0
+    ce0 = rng.standard_normal((B, 1)) * 0.1
+    CI = np.zeros((B, n, m))
+    CI[:, np.arange(n), np.arange(n)] = 1.0
+    CI[:, np.arange(n), n + np.arange(n)] = -1.0
+    ci0 = np.abs(rng.standard_normal((B, m))) * 0.7 + 0.2
+    b = workloads.QPBatch("sparse7", n, 1, m, G, g0, CE, ce0, CI, ci0)
+    assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), "sparse7")
+
+
 def test_full_size_properties(gpu):
     """BASELINE config 2 at full size (1M QPs): size-independent properties instead of the oracle --
     primal feasibility, complementary active set, idempotence across a second launch."""
