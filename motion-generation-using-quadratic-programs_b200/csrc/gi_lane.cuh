@@ -88,9 +88,6 @@
 #ifndef MGQP_LANE_SPLIT_SWEEP
 #define MGQP_LANE_SPLIT_SWEEP 0
 #endif
-#ifndef MGQP_LANE_DIV_GROUPS
-#define MGQP_LANE_DIV_GROUPS 1
-#endif
 #ifndef MGQP_LANE_UNROLLED_SETUP
 #define MGQP_LANE_UNROLLED_SETUP 1
 #endif
@@ -217,61 +214,6 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
   g.s = ss;
   g.xny = d_div(ss, d_add(1.0, cc));
   return g;
-}
-
-// a / b out of line: the unrolled set-up has 63 divisions, inlined they are 16 instructions each plus a slow path
-MGQP_DEV_NOINLINE double ln_div(double a, double b) { return d_div(a, b); }
-// ... and two / three quotients over one divisor per call: independent chains that overlap (the results come back
-// in registers)
-struct LnD2 { double a, b; };
-struct LnD3 { double a, b, c; };
-MGQP_DEV_NOINLINE LnD2 ln_div2(double a0, double a1, double b) {
-  LnD2 r;
-  r.a = d_div(a0, b);
-  r.b = d_div(a1, b);
-  return r;
-}
-MGQP_DEV_NOINLINE LnD3 ln_div3(double a0, double a1, double a2, double b) {
-  LnD3 r;
-  r.a = d_div(a0, b);
-  r.b = d_div(a1, b);
-  r.c = d_div(a2, b);
-  return r;
-}
-// q[0..cnt) /= b in groups of three and two (cnt is a constant once the caller's loop is unrolled)
-template <int K>
-MGQP_DEV void ln_div_all(double (&q)[K], int cnt, double b) {
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    // group starts: 3-groups while more than four remain or exactly three, then 2-groups, then a single
-    int at = 0;
-    bool start = false;
-    int len = 0;
-    while (at <= k && at < cnt) {
-      const int left = cnt - at;
-      len = (left >= 3 && left != 4) ? 3 : (left >= 2 ? 2 : 1);
-#if !MGQP_LANE_DIV_GROUPS
-      len = 1;
-#endif
-      if (at == k) { start = true; break; }
-      at += len;
-    }
-    if (start) {
-      if (len == 3) {
-        if (k + 2 < K) {
-          const LnD3 r = ln_div3(q[k], q[k + 1], q[k + 2], b);
-          q[k] = r.a; q[k + 1] = r.b; q[k + 2] = r.c;
-        }
-      } else if (len == 2) {
-        if (k + 1 < K) {
-          const LnD2 r = ln_div2(q[k], q[k + 1], b);
-          q[k] = r.a; q[k + 1] = r.b;
-        }
-      } else {
-        q[k] = ln_div(q[k], b);
-      }
-    }
-  }
 }
 
 struct LaneIO {  // global memory, this lane's QP
@@ -625,12 +567,15 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
   {
     // Fast path: the whole set-up unrolled over the compile-time N, in registers, touching only the entries the
     // reference's loops produce something from (56 + 56 + 42 multiply-subtracts at N = 7 instead of the 147 + 147
-    // of the row-parallel rolled form below, no loop control, no address arithmetic), divisions out of line.  Same
-    // operations in the same order per element.  It leaves the slot untouched until it knows it can finish: a
-    // factor with inf / NaN in it (a poisoned G) goes to the rolled form, whose full loops spread the poison
-    // exactly as the reference does.
-    double L[N][N];
-    bool bad = false;
+    // of the row-parallel rolled form below, no loop control, no address arithmetic).  Its 77 divisions have only N
+    // distinct divisors -- the pivots -- and run on the split inline path of the division (warp_prims.cuh): one
+    // refinement of 1 / l_ii per pivot, three instructions and a range test per quotient, not a branch in the
+    // whole block.  Same operations in the same order per element.  The block only decides at its end whether its
+    // results stand: a quotient outside the inline path's range (an exact zero in G's factor: sparse G; a tiny or
+    // huge entry), a non-positive pivot, or inf / NaN in the factor (a poisoned G) send the tile to the rolled form,
+    // whose full loops reproduce the reference in every such case.
+    double L[N][N], rl[N];
+    bool bad = false, dok = true;
 #pragma unroll
     for (int i = 0; i < N; i++) {
       double col[N];  // [0]: the pivot; [j - i]: the numerators of L[j][i]
@@ -641,67 +586,55 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
         for (int k = i - 1; k >= 0; k--) sum = msub<FMA>(sum, L[i][k], L[j][k]);
         col[j - i] = sum;
       }
-      if (!bad && col[0] <= 0.0) {
-        bad = true;
-        bad_pivot = col[0];
-      }
+      bad = bad || (col[0] <= 0.0);
       L[i][i] = d_sqrt(col[0]);
+      rl[i] = d_rcp_refined(L[i][i]);
       lfin = lfin && (L[i][i] < INF);
-      {
-        double q[N];
 #pragma unroll
-        for (int j = i + 1; j < N; j++) q[j - i - 1] = col[j - i];
-        ln_div_all<N>(q, N - 1 - i, L[i][i]);
-#pragma unroll
-        for (int j = i + 1; j < N; j++) {
-          L[j][i] = q[j - i - 1];
-          lfin = lfin && (d_abs(L[j][i]) < INF);
-        }
+      for (int j = i + 1; j < N; j++) {
+        L[j][i] = d_div_rcp(col[j - i], L[i][i], rl[i], dok);
+        lfin = lfin && (d_abs(L[j][i]) < INF);
       }
     }
-    if (bad) {
-      fail = true;
-      setup_done = true;
-    } else if (lfin) {
-      setup_done = true;
-      // J = L^-T, row i = forward_elimination(L, e_i); entries left of the diagonal are exactly +0.0 (finite
-      // factor).  Column by column: the r + 1 entries of column r share the divisor L[r][r].
-      double Jv[N][N];
+    // J = L^-T, row i = forward_elimination(L, e_i); entries left of the diagonal are exactly +0.0 (finite factor)
+    double Jd[N];  // the diagonal, for c2
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      double Ji[N];
 #pragma unroll
       for (int r = 0; r < N; r++) {
-        double q[N];
-#pragma unroll
-        for (int i = 0; i <= r; i++) {
+        if (r < i) {
+          Ji[r] = 0.0;
+        } else {
           double acc = (r == i) ? 1.0 : 0.0;
 #pragma unroll
-          for (int j = i; j < r; j++) acc = msub<FMA>(acc, L[r][j], Jv[i][j]);
-          q[i] = acc;
+          for (int j = i; j < r; j++) acc = msub<FMA>(acc, L[r][j], Ji[j]);
+          Ji[r] = d_div_rcp(acc, L[r][r], rl[r], dok);
         }
-        ln_div_all<N>(q, r + 1, L[r][r]);
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-          if (i <= r) Jv[i][r] = q[i];
-          Js[i * N + r] = (i <= r) ? q[i] : 0.0;
-        }
+        Js[i * N + r] = Ji[r];
       }
+      Jd[i] = Ji[i];
+    }
+    // x = -G^-1 g0: forward then backward elimination
+    double y[N], xb[N];
 #pragma unroll
-      for (int i = 0; i < N; i++) c2 = d_add(c2, Jv[i][i]);
-      // x = -G^-1 g0: forward then backward elimination
-      double y[N], xb[N];
+    for (int i = 0; i < N; i++) {
+      double a = g0r[i];
 #pragma unroll
-      for (int i = 0; i < N; i++) {
-        double a = g0r[i];
+      for (int j = 0; j < i; j++) a = msub<FMA>(a, L[i][j], y[j]);
+      y[i] = d_div_rcp(a, L[i][i], rl[i], dok);
+    }
 #pragma unroll
-        for (int j = 0; j < i; j++) a = msub<FMA>(a, L[i][j], y[j]);
-        y[i] = ln_div(a, L[i][i]);
-      }
+    for (int i = N - 1; i >= 0; i--) {
+      double a = y[i];
 #pragma unroll
-      for (int i = N - 1; i >= 0; i--) {
-        double a = y[i];
+      for (int j = i + 1; j < N; j++) a = msub<FMA>(a, L[j][i], xb[j]);
+      xb[i] = d_div_rcp(a, L[i][i], rl[i], dok);
+    }
+    if (dok && lfin && !bad) {
+      setup_done = true;
 #pragma unroll
-        for (int j = i + 1; j < N; j++) a = msub<FMA>(a, L[j][i], xb[j]);
-        xb[i] = ln_div(a, L[i][i]);
-      }
+      for (int i = 0; i < N; i++) c2 = d_add(c2, Jd[i]);
       double fs = 0.0;
 #pragma unroll
       for (int i = 0; i < N; i++) {
