@@ -164,11 +164,12 @@ void mgqp_last_transfer_bytes(int64_t* h2d, int64_t* d2h);
  * uneven work, e.g. the infeasible instances of a scenario sweep); returns the number of devices of that call. */
 int mgqp_last_multi_chunks(int64_t* counts, int max_devices);
 
-/* Self-test of the lane kernel's split division (csrc/warp_prims.cuh: d_rcp_refined / d_div_rcp, the inline path of
- * div.rn.f64 computed branch-free): `count` operand pairs drawn from `seed` (raw bit patterns over the whole exponent
- * range, operands of similar magnitude, pairs sharing a divisor) on the current device.  accepted = pairs the split
- * path answers itself; mismatches = accepted pairs whose quotient differs in any bit from the compiler's own
- * division (must be 0).  Returns MGQP_OK or the CUDA failure. */
+/* Self-test of the lane kernel's split division and square root (csrc/warp_prims.cuh: d_rcp_refined / d_div_rcp /
+ * d_sqrt_split, the inline paths of div.rn.f64 and sqrt.rn.f64 computed branch-free): `count` operand pairs drawn
+ * from `seed` (raw bit patterns over the whole exponent range, operands of similar magnitude, pairs sharing a
+ * divisor) on the current device.  accepted = operations the split paths answer themselves; mismatches = accepted
+ * operations whose result differs in any bit from the compiler's own division / square root (must be 0).
+ * Returns MGQP_OK or the CUDA failure. */
 int mgqp_debug_div_check(int64_t count, uint64_t seed, int64_t* accepted, int64_t* mismatches);
 
 /* Introspection. */

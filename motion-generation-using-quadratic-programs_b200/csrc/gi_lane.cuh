@@ -82,6 +82,12 @@
 #ifndef MGQP_LANE_SWEEP_GROUP
 #define MGQP_LANE_SWEEP_GROUP 3
 #endif
+#ifndef MGQP_LANE_SQRT_SPLIT
+#define MGQP_LANE_SQRT_SPLIT 1
+#endif
+#ifndef MGQP_LANE_GIVENS_CHAIN
+#define MGQP_LANE_GIVENS_CHAIN 0
+#endif
 #ifndef MGQP_LANE_GIVENS_SPLIT
 #define MGQP_LANE_GIVENS_SPLIT 1
 #endif
@@ -142,6 +148,12 @@ MGQP_HOST inline LaneView make_lane_view(int n, int p, int m) {
 // A column may be chosen iff (byte & (EXCL | ACT)) == 0.
 enum { LN_GEN = 0x01, LN_EXCL = 0x02, LN_ACT = 0x04, LN_IDX = 0xf8, LN_IDX_SHIFT = 3 };
 
+#if MGQP_LANE_SQRT_SPLIT
+#define LN_SQRT(v) d_sqrt_split(v, ok)
+#else
+#define LN_SQRT(v) d_sqrt(v)
+#endif
+
 MGQP_DEV double ln_distance(double a, double b) {
   // One division and one square root whichever argument is the larger: the two branches of the reference
   // are the same formula with the arguments swapped, and lanes that disagree on the comparison would
@@ -177,7 +189,7 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
     const bool differ = agt || (b1 > a1);
     const double hi = differ ? (agt ? a1 : b1) : 1.0, lo = differ ? (agt ? b1 : a1) : 1.0;
     const double t = d_div_rcp(lo, hi, d_rcp_refined(hi), ok);
-    const double h = differ ? d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t)))) : d_mul(a1, d_sqrt(2.0));
+    const double h = differ ? d_mul(hi, LN_SQRT(d_add(1.0, d_mul(t, t)))) : d_mul(a1, d_sqrt(2.0));
     const double rh = d_rcp_refined(h);
     double s1 = d_div_rcp(ss, h, rh, ok);
     double c1 = d_div_rcp(cc, h, rh, ok);
@@ -201,6 +213,65 @@ MGQP_DEV_NOINLINE LaneGivens ln_givens(double cc, double ss) {
 #endif
   const double h = ln_distance(cc, ss);
   g.valid = !(d_abs(h) < MGQP_EPS);
+  ss = d_div(ss, h);
+  cc = d_div(cc, h);
+  if (cc < 0.0) {
+    cc = -cc;
+    ss = -ss;
+    g.diag = -h;
+  } else {
+    g.diag = h;
+  }
+  g.c = cc;
+  g.s = ss;
+  g.xny = d_div(ss, d_add(1.0, cc));
+  return g;
+}
+
+// The add_constraint sweep chains its rotations through one number only: rotation j-1 starts from
+// distance(d[j-2], |diag_j|), and |diag_j| is rotation j's hypotenuse.  This call does rotation j's coefficients
+// (given its hypotenuse h) AND rotation j-1's hypotenuse, two independent dependency chains of about equal length
+// in one block of straight-line code, which halves the latency of the sweep.  Same operations on the same operands
+// as ln_givens / ln_distance; the split division's single range test sends the call to their plain forms.
+struct LaneGivensNext {
+  double c, s, xny, diag, hnext;
+  int valid;
+};
+MGQP_DEV_NOINLINE LaneGivensNext ln_givens_next(double cc, double ss, double h, double anext) {
+  LaneGivensNext g;
+  g.valid = !(d_abs(h) < MGQP_EPS);
+  const double bnext = g.valid ? h : cc;  // an invalid rotation leaves d[j-1] what it was
+  {
+    bool ok = true;
+    // rotation j-1's hypotenuse
+    const double a1 = d_abs(anext), b1 = d_abs(bnext);
+    const bool agt = a1 > b1;
+    const bool differ = agt || (b1 > a1);
+    const double hi = differ ? (agt ? a1 : b1) : 1.0, lo = differ ? (agt ? b1 : a1) : 1.0;
+    const double t = d_div_rcp(lo, hi, d_rcp_refined(hi), ok);
+    const double hn = differ ? d_mul(hi, LN_SQRT(d_add(1.0, d_mul(t, t)))) : d_mul(a1, d_sqrt(2.0));
+    // rotation j's coefficients
+    const double rh = d_rcp_refined(h);
+    double s1 = d_div_rcp(ss, h, rh, ok);
+    double c1 = d_div_rcp(cc, h, rh, ok);
+    double dg = h;
+    if (c1 < 0.0) {
+      c1 = -c1;
+      s1 = -s1;
+      dg = -h;
+    }
+    const double den = d_add(1.0, c1);
+    const double xq = d_div_rcp(d_abs(s1), den, d_rcp_refined(den), ok);  // s / den == -((-s) / den) exactly
+    if (ok) {
+      g.c = c1;
+      g.s = s1;
+      g.diag = dg;
+      g.xny = d_signbit(s1) ? -xq : xq;
+      g.hnext = hn;
+      return g;
+    }
+  }
+  g.hnext = ln_distance(anext, bnext);
   ss = d_div(ss, h);
   cc = d_div(cc, h);
   if (cc < 0.0) {
@@ -1157,6 +1228,27 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
                     }
                   }
                 }
+              }
+            }
+          }
+        }
+#elif MGQP_LANE_GIVENS_CHAIN
+        double hcur = 1.0;
+        if (N >= 2 && N - 1 >= iq + 1) hcur = ln_distance_ni(dd[N >= 2 ? N - 2 : 0], dd[N - 1]);
+        for (int j = N - 1; j >= 1; j--) {
+          if (j >= iq + 1) {
+            // (a lane whose sweep ends here hands the call a harmless next operand)
+            const LaneGivensNext g = ln_givens_next(dd[j - 1], dd[j], hcur, (j - 1 >= iq + 1) ? dd[j >= 2 ? j - 2 : 0] : 1.0);
+            hcur = g.hnext;
+            if (g.valid) {
+              dd[j] = 0.0;
+              dd[j - 1] = g.diag;
+#pragma unroll
+              for (int k = 0; k < N; k++) {
+                const double t1 = Jr[k][j - 1], t2 = Jr[k][j];
+                const double n1 = d_add(d_mul(t1, g.c), d_mul(t2, g.s));
+                Jr[k][j - 1] = n1;
+                Jr[k][j] = d_sub(d_mul(g.xny, d_add(t1, n1)), t2);
               }
             }
           }

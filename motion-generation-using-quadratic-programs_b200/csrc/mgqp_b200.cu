@@ -1160,6 +1160,12 @@ __global__ void div_check_kernel(long long count, unsigned long long seed, unsig
       acc++;
       if (__double_as_longlong(q2) != __double_as_longlong(__ddiv_rn(a2, b))) bad++;
     }
+    bool ok3 = true;
+    const double rt = d_sqrt_split(a, ok3);
+    if (ok3) {
+      acc++;
+      if (__double_as_longlong(rt) != __double_as_longlong(__dsqrt_rn(a))) bad++;
+    }
   }
   atomicAdd(out, acc);
   atomicAdd(out + 1, bad);

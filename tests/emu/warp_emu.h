@@ -194,6 +194,12 @@ MGQP_DEV double d_div(double a, double b) { return a / b; }
 MGQP_DEV double d_div_z(double a, double b) { return a / b; }
 // the split inline path of the device's division (warp_prims.cuh): here the quotient is the host's IEEE division and
 // `ok` follows the device's range tests, so that the callers' fallbacks are exercised on the CPU as well
+MGQP_DEV double d_sqrt_split(double x, bool& ok) {
+  unsigned long long u;
+  memcpy(&u, &x, 8);
+  ok = ok && ((unsigned)((unsigned)(u >> 32) - 0x03500000u) < 0x7ca00000u);
+  return sqrt(x);
+}
 MGQP_DEV double d_rcp_refined(double) { return 0.0; }
 MGQP_DEV double d_div_rcp(double a, double b, double, bool& ok) {
   const double q = a / b;
