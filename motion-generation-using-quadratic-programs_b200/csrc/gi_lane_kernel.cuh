@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(256, 1) gi_lane_kernel(const __grid_constant__
     if (tile_next < tiles) {  // pull the next tile's G / g0 towards L2 (phase A of the next round reads them)
       tio.next_G = P.in[0] + tile_next * 32 * P.stride[0];
       tio.next_g0 = P.in[1] + tile_next * 32 * P.stride[1];
+      tio.next_CI = P.in[4] + tile_next * 32 * P.stride[4];
+      tio.next_ci0 = P.in[5] + tile_next * 32 * P.stride[5];
     }
     double xo[N];
     double f;

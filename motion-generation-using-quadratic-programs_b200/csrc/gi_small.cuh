@@ -91,6 +91,10 @@ struct TileOut {   // global-memory outputs, already offset to the first QP of t
   bool fuse_retry = false;
 };
 
+#ifndef MGQP_SMALL_SPLIT_DIV
+#define MGQP_SMALL_SPLIT_DIV 1
+#endif
+
 // sqrt(a^2+b^2) exactly as QuadProg++'s `distance` (weak symbol in QuadProg++.o)
 MGQP_DEV double gi_distance(double a, double b) {
   // One division and one square root whichever argument is the larger: the two branches of the reference
@@ -337,6 +341,11 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       for (int j = 0; j < n; j++, pj += ldJ, pn += nps) dv = mad<FMA>(*pj, *pn, dv);
     }
     if (in_n) sd[li] = dv;
+#if MGQP_SMALL_SPLIT_DIV
+    // refined reciprocals of R's diagonal for the back-substitution below, one per lane (the coefficient row sgx
+    // is free outside add_constraint)
+    if (li < iq) sgx[li] = d_rcp_refined(sR[li * ldR + li]);
+#endif
     wp_sync();
     zv = 0.0;
     if (in_n) {
@@ -351,7 +360,18 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       const double* ri_row = sR + i * ldR;
       MGQP_UNROLL2
       for (int j = i + 1; j < iq; j++) sum = mad<FMA>(ri_row[j], sr[j], sum);
+#if MGQP_SMALL_SPLIT_DIV
+      // This loop is one dependency chain that every lane of the group repeats: the quotient on the split inline
+      // path of the division (warp_prims.cuh) is three dependent operations instead of a dozen, the refinement of
+      // 1 / r_ii having been done off the chain.  Outside that path's range (an exact zero, as sparse problems
+      // produce them all the time) the plain division takes over.
+      const double num = d_sub(sd[i], sum), den = sR[i * ldR + i];
+      bool okq = true;
+      double ri = d_div_rcp(num, den, sgx[i], okq);
+      if (!okq) ri = d_div_z(num, den);
+#else
       const double ri = d_div_z(d_sub(sd[i], sum), sR[i * ldR + i]);
+#endif
       sr[i] = ri;  // same value from every lane of the group
       if (li == i) rv = ri;
     }
@@ -385,11 +405,24 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     // reference's sign normalisation; the incoming d[j] is what rotation j+1 leaves behind.
     const bool myrot = li >= jlo && li <= n - 1 && !((skipm >> li) & 1u);
     const double dprev = (li > 0 && in_n) ? sd[li - 1] : 0.0;
+#if MGQP_SMALL_SPLIT_DIV
+    const double rh = d_rcp_refined(hreg);  // shared by c and s
+    bool okc = true;
+    double c = d_div_rcp(dprev, hreg, rh, okc);
+    if (!okc) c = d_div_z(dprev, hreg);
+#else
     double c = d_div_z(dprev, hreg);
+#endif
     const double dnew = ((skipm >> li) & 1u) ? dprev : ((c < 0.0) ? -hreg : hreg);  // new d[li-1]
     const double dnext = wp_shfl_down(dnew, 1, GW);
     const double din = (li == n - 1) ? sd[n - 1] : dnext;
+#if MGQP_SMALL_SPLIT_DIV
+    bool oks = true;
+    double sn = d_div_rcp(din, hreg, rh, oks);
+    if (!oks) sn = d_div_z(din, hreg);
+#else
     double sn = d_div_z(din, hreg);
+#endif
     if (c < 0.0) {
       c = -c;
       sn = -sn;
@@ -397,7 +430,15 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (myrot) {
       sgc[li] = c;
       sgs[li] = sn;
+#if MGQP_SMALL_SPLIT_DIV
+      const double den = d_add(1.0, c);
+      bool okx = true;
+      double xq = d_div_rcp(sn, den, d_rcp_refined(den), okx);
+      if (!okx) xq = d_div_z(sn, den);
+      sgx[li] = xq;
+#else
       sgx[li] = d_div_z(sn, d_add(1.0, c));
+#endif
     }
     const double dl_rot = wp_shfl(dnew, jlo & (GW - 1), GW);
     const double dlast = (jlo <= n - 1) ? dl_rot : sd[iq < n ? iq : 0];
