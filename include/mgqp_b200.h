@@ -146,6 +146,16 @@ int mgqp_solve_one(int32_t n, int32_t p, int32_t m, const double* G, const doubl
 int mgqp_pack_bound_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI,
                             double* val, int64_t sv, uint8_t* row, int64_t sr, int threads);
 
+/* The same for chunks in which every nonzero coefficient is exactly +1.0 or -1.0 -- every inequality the reference's
+ * caller builds (limitsMatrix = [-I; +I], src/mgqp.cpp:1111-1112): ONE code byte per column (bits 0-5 the row, bit 7
+ * set for -1.0, 0x40 for an all-zero column), code[count][sc].  Returns 1 if the chunk has that form, 0 otherwise.
+ * The host-buffer entry points try this form first (the link then carries 0.9 KB per 7-DoF QP) and expand the codes
+ * into (value, row) pairs on the device; a chunk that does not qualify goes through mgqp_pack_bound_columns.
+ * mgqp_pack_unit_is_fast: 1 iff this CPU has the vector (AVX-512) version; without it the form is not used. */
+int mgqp_pack_unit_columns(int32_t n, int32_t m, int64_t count, const double* CI, int64_t sCI, uint8_t* code, int64_t sc,
+                           int threads);
+int mgqp_pack_unit_is_fast(void);
+
 /* Host threads the packer uses by default: MGQP_HOST_THREADS, else the cores this process may run on.
  * The host-buffer entry points pack CI only when these threads can outrun what the packing saves on
  * the link (one rank per GPU on a 32-core box leaves 4 threads per GPU: dense transport wins there). */

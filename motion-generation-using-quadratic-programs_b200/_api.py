@@ -28,7 +28,7 @@ __all__ = [
     "LogicError", "QPResult", "STATUS", "lib", "lib_path", "solve_quadprog", "solve_quadprog_batched",
     "solve_quadprog_batched_host", "solve_quadprog_batched_multi", "plan", "algorithmic_bytes",
     "kernel_launch_count", "FLAG_FAST_MATH", "FLAG_NO_BULK_COPY", "FLAG_STATIC_SCHEDULE", "FLAG_GROUP_KERNEL", "FLAG_CTA_KERNEL",
-    "FLAG_NO_HOST_PACK", "FLAG_RETRY_WITHOUT_CI", "STATUS_RETRIED", "mgqp_batch", "pack_bound_columns", "last_transfer_bytes",
+    "FLAG_NO_HOST_PACK", "FLAG_RETRY_WITHOUT_CI", "STATUS_RETRIED", "mgqp_batch", "pack_bound_columns", "pack_unit_columns", "last_transfer_bytes",
     "last_multi_chunks", "mgqp_scenarios", "CascadeResult", "solve_cascade_batched", "solve_cascade_batched_host",
 ]
 
@@ -132,6 +132,9 @@ def lib():
         L.mgqp_pack_bound_columns.restype = C.c_int
         L.mgqp_pack_bound_columns.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                               C.c_void_p, C.c_int64, C.c_int]
+        L.mgqp_pack_unit_columns.restype = C.c_int
+        L.mgqp_pack_unit_columns.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                             C.c_int]
         L.mgqp_cascade_batched.restype = C.c_int
         L.mgqp_cascade_batched.argtypes = [C.POINTER(mgqp_scenarios), C.c_int, C.c_void_p]
         L.mgqp_cascade_batched_host.restype = C.c_int
@@ -192,6 +195,16 @@ def pack_bound_columns(CI, threads: int = 0):
     row = np.empty((B, m), dtype=np.uint8)
     ok = lib().mgqp_pack_bound_columns(n, m, B, CI.ctypes.data, n * m, val.ctypes.data, m, row.ctypes.data, m, threads)
     return (val, row) if ok else None
+
+
+def pack_unit_columns(CI, threads: int = 0):
+    """One code byte per column of ``CI [B,n,m]`` when every nonzero coefficient is exactly +-1.0 and no column has
+    two (bits 0-5 the row, bit 7 set for -1.0, 0x40 for an all-zero column): ``code [B,m] uint8``, or ``None``."""
+    CI = np.ascontiguousarray(CI, dtype=np.float64)
+    B, n, m = CI.shape
+    code = np.empty((B, m), dtype=np.uint8)
+    ok = lib().mgqp_pack_unit_columns(n, m, B, CI.ctypes.data, n * m, code.ctypes.data, m, threads)
+    return code if ok else None
 
 
 # ------------------------------------------------------------------ device-resident batches

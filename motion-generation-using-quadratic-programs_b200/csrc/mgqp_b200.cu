@@ -73,6 +73,7 @@ struct DeviceCtx {
   // host-buffer pipeline: two streams and two staging arenas, kept across calls (grow only)
   std::mutex host_mu;
   cudaStream_t host_st[2] = {nullptr, nullptr};
+  cudaEvent_t host_up[2] = {nullptr, nullptr};  // the uploads of the buffer set's current chunk are done
   void* arena[2] = {nullptr, nullptr};
   size_t arena_cap[2] = {0, 0};
   // pinned host staging for the column-compressed CI of one chunk (values, rows), per buffer set
@@ -622,10 +623,25 @@ size_t carve_bufs(DevBufs& b, const mgqp_batch* h, long long chunk, char* base) 
   return off;
 }
 
+// One code byte per inequality column (mgqp_pack_unit_columns) -> the (value, row) pair the solvers read; in place
+// on the row bytes.
+__global__ void unit_code_expand_kernel(long long cnt, int m, int mr, unsigned char* __restrict__ row, double* __restrict__ val) {
+  const long long total = cnt * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long q = e / m;
+    const int i = (int)(e - q * m);
+    const unsigned c = row[q * mr + i];
+    const bool empty = (c & 0x40u) != 0;
+    val[e] = empty ? 0.0 : ((c & 0x80u) ? -1.0 : 1.0);
+    row[q * mr + i] = (unsigned char)(empty ? 0u : (c & 0x3fu));
+  }
+}
+
 // Upload / solve / download QPs [q0, q0+cnt) of host batch h through buffers b on stream st.
 // `pack`: the shape is served by the lane kernel and the caller did not opt out, so CI travels in
 // column-compressed form whenever this chunk qualifies (every column a bound on one variable).
-int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long long cnt, cudaStream_t st, bool pack) {
+int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long long cnt, cudaStream_t st, bool pack,
+              cudaEvent_t uploads_done, bool* try_unit) {
   const long long n = h->n, p = h->p, m = h->m;
   const long long mr = packed_row_stride(m);
   mgqp_batch d = *h;
@@ -646,7 +662,19 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
     d.CI_val = b.CIv; d.CI_row = b.CIr;
     d.sCIv = h->sCIv ? m : 0; d.sCIr = h->sCIr ? mr : 0;
     ci_compressed = true;
-  } else if (m > 0 && pack && b.hCIv &&
+  } else if (m > 0 && pack && b.hCIv && try_unit && *try_unit &&
+             mgqp_pack_unit_columns((int32_t)n, (int32_t)m, cnt, h->CI + q0 * h->sCI, h->sCI, b.hCIr, mr, 0)) {
+    // every coefficient is +-1: one byte per column over the link, expanded on the device
+    CU(cudaMemcpyAsync(b.CIr, b.hCIr, (size_t)(cnt * mr), cudaMemcpyHostToDevice, st));
+    g_h2d_bytes += cnt * mr;
+    const long long total = cnt * m;
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    unit_code_expand_kernel<<<grid, 256, 0, st>>>(cnt, (int)m, (int)mr, b.CIr, b.CIv);
+    g_launches.fetch_add(1);
+    CU(cudaGetLastError());
+    d.CI_val = b.CIv; d.CI_row = b.CIr; d.sCIv = m; d.sCIr = mr;
+    ci_compressed = true;
+  } else if (m > 0 && pack && b.hCIv && ((try_unit && *try_unit) ? (*try_unit = false, true) : true) &&
              mgqp_pack_bound_columns((int32_t)n, (int32_t)m, cnt, h->CI + q0 * h->sCI, h->sCI, b.hCIv, m, b.hCIr, mr, 0)) {
     CU(cudaMemcpyAsync(b.CIv, b.hCIv, (size_t)(cnt * m) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b.CIr, b.hCIr, (size_t)(cnt * mr), cudaMemcpyHostToDevice, st));
@@ -682,6 +710,7 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
       g_h2d_bytes += cnt * f.size * 8;
     }
   }
+  if (uploads_done) CU(cudaEventRecord(uploads_done, st));
   d.x = b.x; d.f = b.f; d.status = b.status;
   d.iq = h->iq ? b.iq : nullptr;
   d.A = h->A ? b.A : nullptr;
@@ -703,7 +732,9 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
 
 long long default_chunk(const mgqp_batch* h) {
   const long long per_qp = mgqp_algorithmic_bytes(h->n, h->p, h->m);
-  long long c = (256ll << 20) / (per_qp > 0 ? per_qp : 1);  // ~256 MB of inputs per chunk
+  // ~128 MB of inputs per chunk (C2: 40k QPs): with the packer and the link about balanced, shorter chunks fill the
+  // two-stage pipeline sooner (32k-64k QPs 5.1e7, 80k 4.9e7, 128k 4.8e7, 256k 4.4e7 QP/s: profiles/r02_notes.md)
+  long long c = (128ll << 20) / (per_qp > 0 ? per_qp : 1);
   if (c < 1024) c = 1024;
   c &= ~1023ll;
   return c;
@@ -724,6 +755,7 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
   const size_t need = carve_bufs(probe, h, chunk, nullptr);
   for (int i = 0; i < 2; i++) {
     if (!ctx->host_st[i]) CU(cudaStreamCreateWithFlags(&ctx->host_st[i], cudaStreamNonBlocking));
+    if (!ctx->host_up[i]) CU(cudaEventCreateWithFlags(&ctx->host_up[i], cudaEventDisableTiming));
     if (ctx->arena_cap[i] < need) {
       if (ctx->arena[i]) CU(cudaFree(ctx->arena[i]));
       ctx->arena[i] = nullptr;
@@ -766,14 +798,19 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     }
   }
   cudaStream_t* st = ctx->host_st;
+  // the one-byte form of +-1 columns is tried until a chunk of this call turns out not to have it
+  bool try_unit = pack && h->n <= 64 && mgqp_pack_unit_is_fast() && !std::getenv("MGQP_NO_UNIT_CODES");
   int k = 0;
   while (!rc) {
     const long long q0 = next->fetch_add(chunk);
     if (q0 >= h->batch) break;
     const long long cnt = (h->batch - q0) < chunk ? (h->batch - q0) : chunk;
-    // the buffer set is reused every second chunk: wait for its previous occupant
-    if (cudaStreamSynchronize(st[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "stream sync failed"); break; }
-    rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1], pack);
+    // The buffer set is reused every second chunk.  Its device buffers are protected by stream order; what the host
+    // has to wait for is only the pinned staging area the packer is about to overwrite, i.e. the UPLOADS of the
+    // set's previous chunk -- not that chunk's kernel and downloads, which a stream synchronisation would add to
+    // the packer's critical path (the call was bound by exactly that path: profiles/r02_notes.md).
+    if (k >= 2 && cudaEventSynchronize(ctx->host_up[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "event sync failed"); break; }
+    rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1], pack, ctx->host_up[k & 1], &try_unit);
     k++;
     if (chunks_done) ++*chunks_done;
   }

@@ -315,7 +315,9 @@ def test_column_compressed_device_input(gpu, restatement):
         assert_bit_identical(r._asdict(), ref, name + " host")
         # G = I and g0 = 0 in every QP (the reference's own caller): one instance per chunk, not per QP
         chunks = [min(1024, B - q) for q in range(0, B, 1024)]
-        assert up == sum(8 * (b.n * b.n + b.n) + c * (8 * (b.n * b.p + b.p + 2 * b.m) + (b.m + 15) // 16 * 16) for c in chunks)
+        from mgqp_b200 import _api
+        vals = 1 if _api.lib().mgqp_pack_unit_is_fast() else 2   # +-1 columns travel as one code byte (AVX-512 hosts)
+        assert up == sum(8 * (b.n * b.n + b.n) + c * (8 * (b.n * b.p + b.p + vals * b.m) + (b.m + 15) // 16 * 16) for c in chunks)
         b.G[B // 2, 3, 3] = 1.25    # one QP with its own G: that chunk ships G per QP again, same answers
         ref = _oracle(restatement, b)
         r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=1024)
@@ -343,8 +345,29 @@ def test_host_pipeline_compressed_transport(gpu, restatement):
     assert_bit_identical(r._asdict(), ref, "dense")
     B, n, p, m = b.batch, b.n, b.p, b.m
     assert up_dense == 8 * B * (n * n + n + n * p + p + n * m + m)
-    assert up_packed == 8 * B * (n * n + n + n * p + p + m + m) + B * ((m + 15) // 16 * 16)
+    from mgqp_b200 import _api
+    unit = bool(_api.lib().mgqp_pack_unit_is_fast())     # +-1 columns: one code byte each (AVX-512 hosts)
+    rows = B * ((m + 15) // 16 * 16)
+    assert up_packed == 8 * B * (n * n + n + n * p + p + m) + rows + (0 if unit else 8 * B * m)
     assert down == B * (8 * n + 8 + 4 + 4 + 4 * (p + m) + 4)
+    if unit:
+        # the (value, row) form of the same batch, and a batch whose later chunks stop being +-1
+        import os
+        os.environ["MGQP_NO_UNIT_CODES"] = "1"
+        try:
+            r = gpu.solve_quadprog_batched_host(*b.fields(), want_active_set=True, chunk=4096)
+            assert gpu.last_transfer_bytes()[0] == up_packed + 8 * B * m
+            assert_bit_identical(r._asdict(), ref, "value-row")
+        finally:
+            del os.environ["MGQP_NO_UNIT_CODES"]
+        b2 = workloads.make("C5", 40001)
+        b2.CI[20000:, :, 7] *= 0.5
+        b2.CI[3, :, 9] = 0.0                     # an empty column and a negative zero stay inside the unit form
+        b2.CI[4, 1, 9] = -0.0
+        r = gpu.solve_quadprog_batched_host(*b2.fields(), want_active_set=True, chunk=4096)
+        up2, _ = gpu.last_transfer_bytes()
+        assert_bit_identical(r._asdict(), _oracle(restatement, b2), "unit then value-row")
+        assert up_packed < up2 < up_packed + 8 * B * m
     # a batch in which only some chunks qualify: QPs 10000.. get a second nonzero in one column
     b.CI[10000:, 2, 5] = 0.25
     ref = _oracle(restatement, b)

@@ -97,3 +97,72 @@ def test_blocks_all_equal(lib):
     c = workloads.make("C2", 5000)
     assert L.mgqp_blocks_all_equal(c.G.ctypes.data, 49, 49, c.batch, 0) == 0
     assert L.mgqp_blocks_all_equal(c.G.ctypes.data, 49, 49, 1, 0) == 1
+
+
+_ISA_SNIPPET = r"""
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r)
+import mgqp_b200
+rng = np.random.default_rng(11)
+h = hashlib.sha256()
+for n, m in [(1, 1), (3, 6), (5, 11), (7, 42), (8, 64), (8, 63), (7, 9)]:
+    B = 301
+    rows = rng.integers(0, n, size=(B, m))
+    vals = rng.standard_normal((B, m))
+    CI = np.zeros((B, n, m))
+    np.put_along_axis(CI, rows[:, None, :], vals[:, None, :], axis=1)
+    CI[::7, :, 0] = 0.0
+    CI[1::7, :, m - 1] = 0.0
+    CI[1::7, n - 1, m - 1] = np.nan
+    CI[2::7][CI[2::7] == 0] = -0.0
+    val, row = mgqp_b200.pack_bound_columns(CI)
+    dec = np.zeros((B, n, m))
+    np.put_along_axis(dec, row[:, None, :].astype(np.int64), val[:, None, :], axis=1)
+    assert np.array_equal(dec, CI, equal_nan=True), (n, m)
+    h.update(val.tobytes()); h.update(row.tobytes())
+    CI[B - 1, 0, m - 1] = 1.0
+    CI[B - 1, n - 1, m - 1] = 2.0
+    if n > 1:
+        assert mgqp_b200.pack_bound_columns(CI) is None, (n, m)
+for n, m in [(1, 1), (3, 6), (7, 42), (8, 64), (8, 63), (14, 28)]:
+    B = 203
+    rows = rng.integers(0, n, size=(B, m))
+    sgn = np.where(rng.integers(0, 2, size=(B, m)) == 1, 1.0, -1.0)
+    CI = np.zeros((B, n, m))
+    np.put_along_axis(CI, rows[:, None, :], sgn[:, None, :], axis=1)
+    CI[::5, :, 0] = 0.0
+    CI[1::5][CI[1::5] == 0] = -0.0
+    code = mgqp_b200.pack_unit_columns(CI)
+    assert code is not None, (n, m)
+    empty = (code & 0x40) != 0
+    assert (empty[::5, 0]).all() and empty.sum() == len(CI[::5])
+    val = np.where(empty, 0.0, np.where(code & 0x80, -1.0, 1.0))
+    dec = np.zeros((B, n, m))
+    np.put_along_axis(dec, np.where(empty, 0, code & 0x3f)[:, None, :].astype(np.int64), val[:, None, :], axis=1)
+    assert np.array_equal(dec, CI), (n, m)
+    h.update(code.tobytes())
+    bad = CI.copy(); bad[B - 1, n - 1, m - 1] = 0.5 if CI[B - 1, n - 1, m - 1] == 0 or True else 0
+    bad[B - 1, :, m - 1] = 0.0; bad[B - 1, n - 1, m - 1] = 0.5          # a non-unit coefficient
+    assert mgqp_b200.pack_unit_columns(bad) is None, (n, m)
+    bad = CI.copy(); bad[0, :, 0] = 0.0; bad[0, 0, 0] = np.nan          # NaN is not a unit
+    assert mgqp_b200.pack_unit_columns(bad) is None, (n, m)
+    if n > 1:
+        bad = CI.copy(); bad[B // 2, :, m // 2] = 0.0; bad[B // 2, 0, m // 2] = 1.0; bad[B // 2, n - 1, m // 2] = -1.0
+        assert mgqp_b200.pack_unit_columns(bad) is None, (n, m)
+print(h.hexdigest())
+"""
+
+
+def test_every_instruction_set_of_the_packer_gives_the_same_bytes(lib):
+    """generic / AVX2 / AVX-512 (picked once per process: one subprocess each; an ISA the CPU lacks falls back)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for isa in ("generic", "avx2", "avx512"):
+        env = dict(os.environ, MGQP_HOST_PACK_ISA=isa)
+        r = subprocess.run([sys.executable, "-c", _ISA_SNIPPET % root], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[isa] = r.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
