@@ -172,6 +172,21 @@ MGQP_DEV double ln_distance(double a, double b) {
 
 MGQP_DEV_NOINLINE double ln_distance_ni(double a, double b) { return ln_distance(a, b); }
 
+// The same value on the split inline paths of the division and the square root (warp_prims.cuh): no convergence
+// region on the way, which is what a serial chain of hypotenuses pays for (the CTA-per-QP kernel's add_constraint
+// runs ~n of them on one thread); outside the inline paths' range the plain form takes over.
+MGQP_DEV double ln_distance_split(double a, double b) {
+  const double a1 = d_abs(a), b1 = d_abs(b);
+  const bool agt = a1 > b1;
+  if (!agt && !(b1 > a1)) return d_mul(a1, d_sqrt(2.0));
+  const double hi = agt ? a1 : b1, lo = agt ? b1 : a1;
+  bool ok = true;
+  const double t = d_div_rcp(lo, hi, d_rcp_refined(hi), ok);
+  const double h = d_mul(hi, d_sqrt_split(d_add(1.0, d_mul(t, t)), ok));
+  if (ok) return h;
+  return ln_distance(a, b);
+}
+
 // (c, s) -> normalised rotation coefficients exactly as add_constraint / delete_constraint derive
 // them (Appendix A).  One shared, non-inlined copy: it holds four IEEE divisions and a square root,
 // and the unrolled sweeps call it from twelve places.  valid == 0 <=> the reference `continue`s.

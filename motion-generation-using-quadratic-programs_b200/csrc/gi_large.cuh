@@ -23,6 +23,10 @@
 // Control flow is uniform across the CTA: thread 0's decisions are broadcast through shared memory.
 #pragma once
 #include "gi_lane.cuh"  // LaneIO, ln_distance, MGQP_LDG, MGQP_EPS
+
+#ifndef MGQP_LARGE_SPLIT_CHAIN
+#define MGQP_LARGE_SPLIT_CHAIN 1
+#endif
 #ifndef MGQP_EMULATE
 #include "gi_large_dmma.cuh"
 #endif
@@ -564,7 +568,11 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
       double carry = (n > 0) ? d_abs(sd[n - 1]) : 0.0;  // |current d[j]|
       MGQP_UNROLL1
       for (int j = n - 1; j >= iq + 1; j--) {
+#if MGQP_LARGE_SPLIT_CHAIN
+        const double h = ln_distance_split(sd[j - 1], carry);
+#else
         const double h = ln_distance(sd[j - 1], carry);
+#endif
         if (d_abs(h) < MGQP_EPS) {
           skip[j] = 1;
           carry = d_abs(sd[j - 1]);

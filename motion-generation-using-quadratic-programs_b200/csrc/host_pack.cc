@@ -218,7 +218,9 @@ class Pool {
   // run job() on `extra` pool threads and on the calling thread
   void run(const std::function<void()>& job, int extra) {
     std::lock_guard<std::mutex> one(call_mu_);
-    if (extra > (int)th_.size()) extra = (int)th_.size();
+    // the pool grows with the largest request it has seen (MGQP_HOST_THREADS may be raised between calls: a rank
+    // that packed with its share of the cores later drives every device of the node on its own)
+    while ((int)th_.size() < extra && (int)th_.size() < 63) th_.emplace_back([this]() { loop(); });
     {
       std::lock_guard<std::mutex> lk(mu_);
       job_ = &job;

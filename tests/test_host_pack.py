@@ -166,3 +166,16 @@ def test_every_instruction_set_of_the_packer_gives_the_same_bytes(lib):
         assert r.returncode == 0, r.stderr[-2000:]
         digests[isa] = r.stdout.strip().splitlines()[-1]
     assert len(set(digests.values())) == 1, digests
+
+
+def test_pool_grows_when_the_thread_budget_is_raised(lib, monkeypatch):
+    """A torchrun rank packs with its share of the cores first and may drive every device later (bench.py's
+    multi-device record): the pool must follow MGQP_HOST_THREADS upwards."""
+    b = workloads.make("C2", 20000)
+    monkeypatch.setenv("MGQP_HOST_THREADS", "2")
+    first = lib.pack_bound_columns(b.CI)
+    monkeypatch.setenv("MGQP_HOST_THREADS", "7")
+    second = lib.pack_bound_columns(b.CI)
+    third = lib.pack_bound_columns(b.CI, threads=11)
+    for out in (second, third):
+        assert np.array_equal(out[0], first[0]) and np.array_equal(out[1], first[1])
