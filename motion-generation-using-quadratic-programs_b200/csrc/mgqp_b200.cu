@@ -732,9 +732,12 @@ int run_chunk(const mgqp_batch* h, int device, DevBufs& b, long long q0, long lo
 
 long long default_chunk(const mgqp_batch* h) {
   const long long per_qp = mgqp_algorithmic_bytes(h->n, h->p, h->m);
-  // ~128 MB of inputs per chunk (C2: 40k QPs): with the packer and the link about balanced, shorter chunks fill the
-  // two-stage pipeline sooner (32k-64k QPs 5.1e7, 80k 4.9e7, 128k 4.8e7, 256k 4.4e7 QP/s: profiles/r02_notes.md)
-  long long c = (128ll << 20) / (per_qp > 0 ? per_qp : 1);
+  // 48k QPs per chunk, at most ~512 MB of inputs.  Measured (profiles/r02_notes.md 2c): the 7-variable shapes run
+  // best at 32k-64k QPs per chunk (5.1e7 QP/s; 80k 4.9e7, 256k 4.4e7: shorter chunks fill the two-stage pipeline
+  // sooner), the 14-variable ones want at least ~40k (S0: 8k 1.1e7, 21k 1.7e7, 42k 1.9e7 QP/s: per-chunk launch and
+  // copy submission costs).
+  long long c = (512ll << 20) / (per_qp > 0 ? per_qp : 1);
+  if (c > 49152) c = 49152;
   if (c < 1024) c = 1024;
   c &= ~1023ll;
   return c;
@@ -809,6 +812,8 @@ int pump(const mgqp_batch* h, int device, long long chunk, std::atomic<long long
     // has to wait for is only the pinned staging area the packer is about to overwrite, i.e. the UPLOADS of the
     // set's previous chunk -- not that chunk's kernel and downloads, which a stream synchronisation would add to
     // the packer's critical path (the call was bound by exactly that path: profiles/r02_notes.md).
+    static const bool full_sync = std::getenv("MGQP_HOST_STREAM_SYNC") != nullptr;  // A/B knob: the former behaviour
+    if (full_sync && cudaStreamSynchronize(st[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "stream sync failed"); break; }
     if (k >= 2 && cudaEventSynchronize(ctx->host_up[k & 1]) != cudaSuccess) { rc = fail(MGQP_ERR_CUDA, "event sync failed"); break; }
     rc = run_chunk(h, device, bufs[k & 1], q0, cnt, st[k & 1], pack, ctx->host_up[k & 1], &try_unit);
     k++;
