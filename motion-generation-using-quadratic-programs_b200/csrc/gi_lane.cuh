@@ -55,6 +55,8 @@
 #define MGQP_PREFETCH_L2(p) do { } while (0)
 #define MGQP_PREFETCH_L2_KEEP(p) do { } while (0)
 #define MGQP_CP8(dst, src) (*(dst) = *(src))
+#define MGQP_CP8_AT(sbase, base, off, src) ((base)[off] = *(src))
+#define MGQP_SHARED_BASE(p) 0u
 #define MGQP_CP_WAIT() do { } while (0)
 #define MGQP_OPAQUE_PTR(p) do { } while (0)
 #else
@@ -68,6 +70,10 @@
 #define MGQP_LDG2_STREAM(p, a, b) asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p))
 // 8-byte asynchronous copy global -> shared: no register, no scoreboard; completion by MGQP_CP_WAIT
 #define MGQP_CP8(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+// the same with the 32-bit shared-window address of `base` taken once outside the loop (the conversion costs four
+// uniform-datapath instructions each time it is rematerialised)
+#define MGQP_SHARED_BASE(p) ((unsigned)__cvta_generic_to_shared(p))
+#define MGQP_CP8_AT(sbase, base, off, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((sbase) + 8u * (unsigned)(off)), "l"(src) : "memory")
 #define MGQP_CP_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #endif
 
@@ -87,6 +93,9 @@
 // (231 KB of shared memory per CTA, 13 KB less L1) and every flag change pays a refresh.  Off.
 #ifndef MGQP_LANE_EFF_BYTE
 #define MGQP_LANE_EFF_BYTE 0
+#endif
+#ifndef MGQP_LANE_GEN_AFTER
+#define MGQP_LANE_GEN_AFTER 1
 #endif
 #ifndef MGQP_LANE_PREFETCH_NEXT_CI
 #define MGQP_LANE_PREFETCH_NEXT_CI 0  // measured: 1 = -3 %, 2 = -9 % (the lines are evicted before phase B wants them)
@@ -512,6 +521,10 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
     int doff = q * v.stride + c;
     const int dstep = dq * v.stride + dc, dwrap = v.stride - m;
     const unsigned de = 32 + dq * (N - 1) * m, ewrap = (N - 1) * m;
+    const unsigned sdci0 = MGQP_SHARED_BASE(dci0);
+    (void)sdci0;
+    unsigned seen_gen = 0;
+    (void)seen_gen;
     constexpr int K = MGQP_LANE_K;               // columns per trip; two trips (2*K*N loads) in flight per lane
     struct Trip { double b[K][N]; int c[K], doff[K]; unsigned t[K]; };
     auto load = [&](Trip& T, int r0) {
@@ -539,12 +552,16 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
             d_or_if_nonzero(mask, T.b[u][j], 1u << j);
           }
           const unsigned byte = ln_column_byte<N>(mask, val);
-          MGQP_CP8(dci0 + T.doff[u], ci0 + T.t[u]);
+          MGQP_CP8_AT(sdci0, dci0, T.doff[u], ci0 + T.t[u]);
           bytes[8 * T.doff[u] - 7 * T.c[u]] = (unsigned char)byte;
 #if MGQP_LANE_EFF_BYTE
           bytes[8 * T.doff[u] - 7 * T.c[u] + m] = (unsigned char)(byte >> LN_IDX_SHIFT);
 #endif
+#if MGQP_LANE_GEN_AFTER
+          seen_gen |= byte;   // (bit 0 = LN_GEN) the owners' flags are set after the loop, and only if there is one
+#else
           if (byte & LN_GEN) gen[8 * (T.doff[u] - T.c[u])] = 1;
+#endif
         }
       }
     };
@@ -558,6 +575,18 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
       sort(B, r0 + K);
     }
     MGQP_CP_WAIT();
+#if MGQP_LANE_GEN_AFTER
+    // general columns are the exception (none in anything the reference builds): only a warp that met one pays for
+    // telling the owners -- every lane then looks through its own QP's bytes
+    if (wp_any((seen_gen & LN_GEN) != 0)) {
+      wp_sync();
+      const unsigned char* mine = bytes + (size_t)lane * v.stride * 8;
+      bool g = false;
+#pragma unroll 1
+      for (int i = 0; i < m; i++) g = g || (mine[i] & LN_GEN);
+      if (g) gen[(size_t)lane * v.stride * 8] = 1;
+    }
+#endif
     return;
   }
   LaneWalk w;                                  // source offsets: the ci0 block ([q][c], stride sci0)
