@@ -94,6 +94,11 @@
 #ifndef MGQP_LANE_EFF_BYTE
 #define MGQP_LANE_EFF_BYTE 0
 #endif
+// 1 = ci0 is loaded with the column's rows and stored, instead of a cp.async per column (which ptxas pads with
+// three no-ops).  Measured: 7.485 against 7.430 ms.  Off.
+#ifndef MGQP_LANE_CI0_LDG
+#define MGQP_LANE_CI0_LDG 0
+#endif
 #ifndef MGQP_LANE_GEN_AFTER
 #define MGQP_LANE_GEN_AFTER 1
 #endif
@@ -432,7 +437,7 @@ MGQP_DEV void ln_stage_G(const LaneView& v, double* __restrict__ ws, const LaneT
       double* dst = ws + v.oLs;
 #pragma unroll 7
       for (int r = 0; r < L; r++) {  // 32 * N*N elements = N*N rounds of 32 lanes
-        MGQP_CP8(dst + doff, src + 32 * r);
+        MGQP_CP8(dst + doff, src + 32 * r);   // (taking the shared-window base once, as phase B does: 0.4 % slower here)
         k += dk; doff += dstep;
         if (k >= L) { k -= L; doff += dwrap; }
       }
@@ -526,14 +531,23 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
     unsigned seen_gen = 0;
     (void)seen_gen;
     constexpr int K = MGQP_LANE_K;               // columns per trip; two trips (2*K*N loads) in flight per lane
+#if MGQP_LANE_CI0_LDG
+    struct Trip { double b[K][N]; double c0[K]; int c[K], doff[K]; };   // c0: the column's ci0, loaded with its rows
+#else
     struct Trip { double b[K][N]; int c[K], doff[K]; unsigned t[K]; };
+#endif
     auto load = [&](Trip& T, int r0) {
 #pragma unroll
       for (int u = 0; u < K; u++) {
         if (r0 + u < m) {  // warp-uniform
 #pragma unroll
           for (int j = 0; j < N; j++) T.b[u][j] = MGQP_LDG(rowp[j] + e);
+#if MGQP_LANE_CI0_LDG
+          T.c0[u] = MGQP_LDG(ci0 + tt);
+          T.c[u] = c; T.doff[u] = doff;
+#else
           T.c[u] = c; T.doff[u] = doff; T.t[u] = tt;
+#endif
           tt += 32; c += dc; e += de; doff += dstep;
           if (c >= m) { c -= m; e += ewrap; doff += dwrap; }
         }
@@ -552,7 +566,11 @@ MGQP_DEV void ln_stage_CI(const LaneView& v, double* __restrict__ ws, const Lane
             d_or_if_nonzero(mask, T.b[u][j], 1u << j);
           }
           const unsigned byte = ln_column_byte<N>(mask, val);
+#if MGQP_LANE_CI0_LDG
+          dci0[T.doff[u]] = T.c0[u];   // (a cp.async here costs four issue slots: ptxas pads each with three no-ops)
+#else
           MGQP_CP8_AT(sdci0, dci0, T.doff[u], ci0 + T.t[u]);
+#endif
           bytes[8 * T.doff[u] - 7 * T.c[u]] = (unsigned char)byte;
 #if MGQP_LANE_EFF_BYTE
           bytes[8 * T.doff[u] - 7 * T.c[u] + m] = (unsigned char)(byte >> LN_IDX_SHIFT);
