@@ -948,8 +948,9 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
     for (int i = 0; i < N; i++)
 #pragma unroll
       for (int j = 0; j < N; j++) Jr[i][j] = Js[i * N + j];
-#pragma unroll 1
-    for (int i = 0; i < lane_rh_size(N); i++) R[i] = 0.0;
+    constexpr int RH = (N - 1) * N - ((N - 1) * (N - 2)) / 2 + N;  // lane_rh_size(N)
+#pragma unroll
+    for (int i = 0; i < RH; i++) R[i] = 0.0;  // (rolled, this was six instructions per store)
     S[v.ozero] = 0.0;
 #if MGQP_LANE_EFF_BYTE
     S[v.oinf] = INF;
@@ -1165,12 +1166,19 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
           for (int i = 0; i < N; i++) z[i] = mad<FMA>(Jr[i][j], dd[j], z[i]);
         }
       }
+      {
+        // row i of the packed R starts at MGQP_RH(i, 0) = i*N - i(i-1)/2: a running offset instead of the index
+        // arithmetic per element
+        int row = MGQP_RH(iq, 0);
 #pragma unroll 1
-      for (int i = iq - 1; i >= 0; i--) {
-        double s = 0.0;
+        for (int i = iq - 1; i >= 0; i--) {
+          row -= N - i;  // MGQP_RH(i + 1, 0) - MGQP_RH(i, 0) = N - i
+          const double* Ri = R + row;
+          double s = 0.0;
 #pragma unroll 1
-        for (int j = i + 1; j < iq; j++) s = mad<FMA>(R[MGQP_RH(i, j)], sr[j], s);
-        sr[i] = d_div(d_sub(sd[i], s), R[MGQP_RH(i, i)]);
+          for (int j = i + 1; j < iq; j++) s = mad<FMA>(Ri[j], sr[j], s);
+          sr[i] = d_div(d_sub(sd[i], s), Ri[i]);
+        }
       }
       double zz = 0.0, znp = 0.0;
 #pragma unroll
@@ -1421,7 +1429,7 @@ MGQP_DEV void gi_lane_tile(const LaneView& v, double* __restrict__ ws, const Lan
         for (int i = 0; i < N; i++) sd[i] = dd[i];
         iq++;
 #pragma unroll 1
-        for (int i = 0; i < iq; i++) R[MGQP_RH(i, iq - 1)] = sd[i];
+        for (int i = 0, off = iq - 1; i < iq; off += N - i, i++) R[off] = sd[i];  // off = MGQP_RH(i, iq - 1)
         const double dl = d_abs(sd[iq - 1]);
         bool ok = true;
         if (dl <= d_mul(MGQP_EPS, R_norm)) ok = false;
