@@ -41,7 +41,7 @@
 #define MGQP_UNROLL16 _Pragma("unroll 16")
 #define MGQP_UNROLL4 _Pragma("unroll 4")
 #ifndef MGQP_SETUP_DEPTH
-#define MGQP_SETUP_DEPTH 8
+#define MGQP_SETUP_DEPTH 16  // loads in flight per thread in the set-up loops: 8 -> 16 +1.2 %, 32 the same
 #endif
 #define MGQP_PRAGMA_(x) _Pragma(#x)
 #define MGQP_PRAGMA(x) MGQP_PRAGMA_(x)
