@@ -105,6 +105,16 @@ MGQP_DEV double gi_distance(double a, double b) {
   const bool agt = a1 > b1;
   if (!agt && !(b1 > a1)) return d_mul(a1, d_sqrt(2.0));
   const double hi = agt ? a1 : b1, lo = agt ? b1 : a1;
+#if MGQP_SMALL_SPLIT_DIV
+  // the chain of hypotenuses is serial and every lane of the group repeats it: no convergence region on the way
+  // (split inline paths of the division and the square root); zeros and out-of-range operands take the plain form
+  {
+    bool ok = true;
+    const double t = d_div_rcp(lo, hi, d_rcp_refined(hi), ok);
+    const double h = d_mul(hi, d_sqrt_split(d_add(1.0, d_mul(t, t)), ok));
+    if (ok) return h;
+  }
+#endif
   const double t = d_div_z(lo, hi);  // distance(0, h) is the common case on sparse problems
   return d_mul(hi, d_sqrt(d_add(1.0, d_mul(t, t))));
 }
