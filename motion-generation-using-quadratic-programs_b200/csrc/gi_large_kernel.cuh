@@ -20,7 +20,14 @@ struct LargeParams {
 };
 
 template <bool FMA>
-__global__ void __launch_bounds__(512, 1) gi_large_kernel(const __grid_constant__ LargeParams P) {
+// 384 threads x 2 CTAs per SM (80 registers, a few spills) against 256 x 2 (124 registers): the row-per-thread
+// passes of the 350-variable MPC shape get one row per thread instead of two for 94 of 256 threads, the scan six
+// passes instead of nine.  Measured on C4: exact mode +2.3 %, MGQP_FLAG_FAST_MATH +9 %; 352 / 416 / 448 threads lose.
+#ifndef MGQP_LARGE_BOUNDS_T
+#define MGQP_LARGE_BOUNDS_T 384
+#define MGQP_LARGE_BOUNDS_B 2
+#endif
+__global__ void __launch_bounds__(MGQP_LARGE_BOUNDS_T, MGQP_LARGE_BOUNDS_B) gi_large_kernel(const __grid_constant__ LargeParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long s_next;
   double* ws = P.workspace + (size_t)blockIdx.x * P.v.ws_doubles;

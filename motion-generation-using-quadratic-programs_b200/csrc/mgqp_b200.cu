@@ -280,6 +280,11 @@ LargePlan make_large_plan(int n, int p, int m, int smem_optin) {
   int tmax = 256;
   if (const char* e = std::getenv("MGQP_LARGE_T")) tmax = std::atoi(e);  // tuning knob
   while (T < want && T < tmax) T *= 2;
+  if (want > 256 && tmax >= 256) T = 384;  // (gi_large_kernel.cuh: launch bounds 384 x 2)
+  if (const char* e = std::getenv("MGQP_LARGE_T_EXACT")) {  // tuning knob: any multiple of 32
+    const int t = std::atoi(e);
+    if (t >= 32 && t <= 384 && t % 32 == 0) T = t;
+  }
   lp.T = T;
   lp.v = make_large_view(n, p, m, T);
   lp.ok = lp.v.smem_bytes + 1024 <= smem_optin && (long long)n * n < (1ll << 30);
