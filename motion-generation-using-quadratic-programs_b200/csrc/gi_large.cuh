@@ -24,6 +24,9 @@
 #pragma once
 #include "gi_lane.cuh"  // LaneIO, ln_distance, MGQP_LDG, MGQP_EPS
 
+#ifndef MGQP_LARGE_GB
+#define MGQP_LARGE_GB 8  // columns of J fetched ahead in add_constraint's row pass (at 80 registers: 8 -> 16 -2 %, 32 -12 %)
+#endif
 #ifndef MGQP_LARGE_SPLIT_CHAIN
 #define MGQP_LARGE_SPLIT_CHAIN 1
 #endif
@@ -629,10 +632,10 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     for (int k = tid; k < n; k += T) {
       double* Jk = J + k;  // row k of J, element j at Jk[j * n]: coalesced across the threads
       double t2 = Jk[(size_t)(n - 1) * n];
-      // The original entries J[k][j-1] do not depend on the rotations: they are fetched sixteen columns ahead of
+      // The original entries J[k][j-1] do not depend on the rotations: they are fetched MGQP_LARGE_GB columns ahead of
       // their use.  (Written as one load and one store per trip, the loop waited a full memory round trip per
       // rotation -- ~300 of them per sweep: the stores to the same array keep the compiler from hoisting the loads.)
-      constexpr int GB = 16;
+      constexpr int GB = MGQP_LARGE_GB;
       int j = n - 1;
       MGQP_UNROLL1
       for (; j - GB >= iq; j -= GB) {
