@@ -92,10 +92,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def wait_ready(self, timeout: float = 5.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up can outlast a 20 ms timed region)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self) -> int:
+        """Index of the next sample: pass it to stop() to keep only the samples taken from here on."""
+        return len(self.lines)
+
+    def stop(self, first: int = 0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(1.5e-3 * self.period_ms)  # let the sample in flight arrive; longer would only add idle samples
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -103,7 +113,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[first:] or self.lines  # (the region was shorter than one period: the nearest samples)
+        for ln in lines:
             c = [v.strip() for v in ln.split(",")]
             if len(c) < 9:
                 continue
@@ -532,11 +543,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The timed region is K launches of ~2 ms: shorter than nvidia-smi's start-up and hardly longer than its sampling
+    # period.  So the sampler starts first and the SAME launches run untimed until its first sample is in (pre-roll),
+    # and again for ~120 ms after the timed region (post-roll): the clocks reported are those of this load, taken from
+    # the start of the timed region on.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_pre = time.perf_counter()
+    while sampler.proc and not sampler.lines and time.perf_counter() - t_pre < 5.0:
+        mgqp_b200.solve_quadprog_batched(*dev_in, flags=args.flags, out=out)
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         mgqp_b200.solve_quadprog_batched(*dev_in, flags=args.flags, out=out)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    first_sample = sampler.mark()
     l0 = mgqp_b200.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
@@ -546,7 +566,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     launches = mgqp_b200.kernel_launch_count() - l0
     total_ms = ev[0].elapsed_time(ev[-1])
-    clocks = sampler.stop()  # sampled every 20 ms over the device-resident timed region
+    t_post = time.perf_counter()
+    while time.perf_counter() - t_post < 0.12:   # post-roll (untimed, after the launch count was taken)
+        mgqp_b200.solve_quadprog_batched(*dev_in, flags=args.flags, out=out)
+        torch.cuda.synchronize()
+    clocks = sampler.stop(first_sample)  # every 20 ms from the start of the timed region through the post-roll
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     value = sharding.whole_job_rate(B * args.steps, total_ms / 1e3)  # all ranks' QPs / max-over-ranks device time
     ms_per_step = world * B * 1e3 / value
@@ -562,15 +586,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # (the e2e leg is bound by the host cores and the link, and a 20 ms nvidia-smi poll takes driver locks its
     # copies wait on -- measured: 3.8e7 against 4.9e7 QP/s -- so this leg is sampled at a gentler period)
     sampler2 = ClockSampler(local_rank, period_ms=args.e2e_clock_ms) if args.e2e_clock_ms > 0 else None
-    barrier()
     if sampler2:
         sampler2.start()
+        sampler2.wait_ready()
+    barrier()
+    first_sample2 = sampler2.mark() if sampler2 else 0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         mgqp_b200.solve_quadprog_batched_host(*host_np, device=local_rank, flags=args.flags, out=res)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_clocks = sampler2.stop() if sampler2 else None
+    e2e_clocks = sampler2.stop(first_sample2) if sampler2 else None
     e2e_value = sharding.whole_job_rate(B * e2e_steps, e2e_s)
     # bytes that actually crossed the link in the last call (the library counts its own copies): where a
     # chunk's CI is a set of bounds it travels column-compressed (m*9 bytes, mgqp_batch::CI_val) instead
