@@ -60,7 +60,11 @@
 
 namespace mgqp {
 
-#define MGQP_ROWBLK 8
+// rows of R / L staged per block for the serial solves.  1 keeps the CTA's shared memory at 43 KB for the 350-variable
+// shape, which is what lets five CTAs share an SM (gi_large_kernel.cuh).
+#ifndef MGQP_ROWBLK
+#define MGQP_ROWBLK 1
+#endif
 #ifndef MGQP_ELL_K
 #define MGQP_ELL_K 64
 #endif
@@ -283,7 +287,11 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
   double c1 = 0.0, c2 = 0.0, R_norm = 1.0;
   bool dense_done = false;
 #ifndef MGQP_EMULATE
-  if (FMA && n >= 128) {
+  // scratch of the tensor-core set-up: 8 (n + 16) + 64 (warps + 2) doubles -- the row buffer if it is large enough,
+  // else the block of n-vectors in front of it (none of them is live before the set-up has finished)
+  const int dmma_need = 8 * (n + 16) + 64 * ((T >> 5) + 2);
+  double* dmma_scratch = (2 * MGQP_ROWBLK * n >= dmma_need) ? srow : ((v.ored - v.ox >= dmma_need) ? sm + v.ox : nullptr);
+  if (FMA && n >= 128 && dmma_scratch != nullptr) {
     // MGQP_FLAG_FAST_MATH: the dense set-up on the fp64 tensor cores (gi_large_dmma.cuh)
     dense_done = true;
     MGQP_UNROLL1
@@ -299,7 +307,7 @@ MGQP_DEV void gi_large_solve(const LargeView& v, unsigned char* smem, double* ws
     blk_sync();
     double bad = 0.0;
     if (tid == 0) sbc[2] = 0.0;
-    const bool okf = large_setup_dmma(n, io.G, Gc, J, srow, &sbc[2]);
+    const bool okf = large_setup_dmma(n, io.G, Gc, J, dmma_scratch, &sbc[2]);
     blk_sync();
     if (!okf) {
       fail = true;

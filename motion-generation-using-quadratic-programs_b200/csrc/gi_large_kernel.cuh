@@ -20,12 +20,16 @@ struct LargeParams {
 };
 
 template <bool FMA>
-// 384 threads x 2 CTAs per SM (80 registers, a few spills) against 256 x 2 (124 registers): the row-per-thread
-// passes of the 350-variable MPC shape get one row per thread instead of two for 94 of 256 threads, the scan six
-// passes instead of nine.  Measured on C4: exact mode +2.3 %, MGQP_FLAG_FAST_MATH +9 %; 352 / 416 / 448 threads lose.
+// CTA shape.  Half of this kernel's stall cycles are block barriers: threads waiting for thread 0's serial chains (the
+// hypotenuse chain of add_constraint, the back-substitution of update_r -- both fixed by the reference's operation
+// order) or for the slowest row of a pass.  What fills those waits is OTHER QPs on the same SM, so the CTA is made
+// small: 128 threads, 96 registers, 43 KB of shared memory (MGQP_ROWBLK = 1) -> five CTAs per SM.  Measured on the
+// 350-variable MPC shape (2368 QPs, exact / MGQP_FLAG_FAST_MATH QP/s; profiles/r02_notes.md):
+//   256 x 2: 4 221 / 4 683     384 x 2: 4 434 / 5 042     256 x 3: 4 615 / 5 130     224 x 3: 4 740 / 5 297
+//   192 x 4: 5 343 / 5 942     160 x 4: 4 532 / 5 049     128 x 5: 5 449 / 6 080
 #ifndef MGQP_LARGE_BOUNDS_T
-#define MGQP_LARGE_BOUNDS_T 384
-#define MGQP_LARGE_BOUNDS_B 2
+#define MGQP_LARGE_BOUNDS_T 128
+#define MGQP_LARGE_BOUNDS_B 5
 #endif
 __global__ void __launch_bounds__(MGQP_LARGE_BOUNDS_T, MGQP_LARGE_BOUNDS_B) gi_large_kernel(const __grid_constant__ LargeParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -277,13 +277,13 @@ LargePlan make_large_plan(int n, int p, int m, int smem_optin) {
   LargePlan lp;
   int want = n > (m + 3) / 4 ? n : (m + 3) / 4;
   int T = 64;
-  int tmax = 256;
+  int tmax = 128;  // (gi_large_kernel.cuh: launch bounds 128 x 5 -- small CTAs, many per SM)
   if (const char* e = std::getenv("MGQP_LARGE_T")) tmax = std::atoi(e);  // tuning knob
+  if (tmax > MGQP_LARGE_BOUNDS_T) tmax = MGQP_LARGE_BOUNDS_T;
   while (T < want && T < tmax) T *= 2;
-  if (want > 256 && tmax >= 256) T = 384;  // (gi_large_kernel.cuh: launch bounds 384 x 2)
   if (const char* e = std::getenv("MGQP_LARGE_T_EXACT")) {  // tuning knob: any multiple of 32
     const int t = std::atoi(e);
-    if (t >= 32 && t <= 384 && t % 32 == 0) T = t;
+    if (t >= 32 && t <= MGQP_LARGE_BOUNDS_T && t % 32 == 0) T = t;
   }
   lp.T = T;
   lp.v = make_large_view(n, p, m, T);
@@ -304,7 +304,7 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, lp.T, lp.v.smem_bytes));
   if (per_sm < 1) return fail(MGQP_ERR_UNSUPPORTED_SHAPE, "CTA-per-QP kernel does not fit an SM (smem %d B)", lp.v.smem_bytes);
-  int cap_sm = 2;
+  int cap_sm = MGQP_LARGE_BOUNDS_B;
   if (const char* e = std::getenv("MGQP_LARGE_CTAS_PER_SM")) cap_sm = std::atoi(e);  // tuning knob
   if (per_sm > cap_sm) per_sm = cap_sm;
   long long ctas = (long long)ctx->sms * per_sm;
