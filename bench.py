@@ -310,8 +310,9 @@ def c4_record(mgqp_b200, dev, peak, B):
                                       "active_sets_equal": bool(torch.equal(out_fast.A, out.A)),
                                       "x_rel_max": relx, "f_rel_max": relf, "within_1e-9": bool(relx <= 1e-9 and relf <= 1e-9)}}
     del out_fast
-    # whole waves of the resident CTAs (five per SM, gi_large_kernel.cuh), so that the set-up's rate is not quantised
-    Bd = min(B, 4 * 5 * torch.cuda.get_device_properties(dev).multi_processor_count)
+    # whole waves of the resident CTAs (four per SM for this shape, gi_large_kernel.cuh), so that the set-up's rate is
+    # not quantised
+    Bd = min(B, 4 * 4 * torch.cuda.get_device_properties(dev).multi_processor_count)
     z = lambda *sh: torch.zeros(sh, dtype=torch.float64, device=dev)
     bare = [t[0][:Bd], t[1][:Bd], z(Bd, n, 0), z(Bd, 0), z(Bd, n, 0), z(Bd, 0)]
     dense_ms, _ = timed_launches(mgqp_b200, bare, 2, 1, 16)

@@ -60,8 +60,8 @@
 
 namespace mgqp {
 
-// rows of R / L staged per block for the serial solves.  1 keeps the CTA's shared memory at 43 KB for the 350-variable
-// shape, which is what lets five CTAs share an SM (gi_large_kernel.cuh).
+// rows of R / L staged per block for the serial solves.  1 keeps the CTA's shared memory at 49 KB for the 350-variable
+// shape, which is what lets four CTAs share an SM (gi_large_kernel.cuh).
 #ifndef MGQP_ROWBLK
 #define MGQP_ROWBLK 1
 #endif

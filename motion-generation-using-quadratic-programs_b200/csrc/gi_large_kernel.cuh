@@ -23,10 +23,13 @@ template <bool FMA>
 // CTA shape.  Half of this kernel's stall cycles are block barriers: threads waiting for thread 0's serial chains (the
 // hypotenuse chain of add_constraint, the back-substitution of update_r -- both fixed by the reference's operation
 // order) or for the slowest row of a pass.  What fills those waits is OTHER QPs on the same SM, so the CTA is made
-// small: 128 threads, 96 registers, 43 KB of shared memory (MGQP_ROWBLK = 1) -> five CTAs per SM.  Measured on the
-// 350-variable MPC shape (2368 QPs, exact / MGQP_FLAG_FAST_MATH QP/s; profiles/r02_notes.md):
+// small: 128 threads, 96 registers (five CTAs per SM by registers), 49 KB of shared memory for the 350-variable shape
+// (MGQP_ROWBLK = 1), which admits FOUR of them.  Measured on that shape (2368 QPs, exact / MGQP_FLAG_FAST_MATH QP/s;
+// profiles/r02_notes.md):
 //   256 x 2: 4 221 / 4 683     384 x 2: 4 434 / 5 042     256 x 3: 4 615 / 5 130     224 x 3: 4 740 / 5 297
-//   192 x 4: 5 343 / 5 942     160 x 4: 4 532 / 5 049     128 x 5: 5 449 / 6 080
+//   192 x 4: 5 343 / 5 942     160 x 4: 4 532 / 5 049     128 x 4: 5 449 / 6 080
+// (With x_old / u_old moved to the global workspace the CTA shrinks to 43 KB and five fit: 5 156 / 5 748 against
+// 5 107 / 5 661 for four on the same box -- within the noise, not kept.)
 #ifndef MGQP_LARGE_BOUNDS_T
 #define MGQP_LARGE_BOUNDS_T 128
 #define MGQP_LARGE_BOUNDS_B 5
