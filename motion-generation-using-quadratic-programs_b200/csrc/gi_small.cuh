@@ -41,6 +41,7 @@ struct TileView {
   int n, p, m;
   int qpw;                               // QPs per warp = 32 / GW
   int oG, og0, oCE, oce0, oCI, oci0;     // input block, field-major; QP stride = natural size
+  int ci_comp, cisz;                     // CI kept column-compressed in shared memory (values | rows); doubles per QP
   int oWork, wstride;                    // work block, QP-major
   int wJ, wR, wx, wd, wr, wred, wgc, wgs, wgx;  // offsets inside one QP's work block
   int ldJ, ldR;
@@ -50,10 +51,15 @@ struct TileView {
 MGQP_HD inline int mgqp_even(int v) { return (v + 1) & ~1; }
 
 // Host-side (and emulator-side) construction of the plan.
-MGQP_HOST inline TileView make_tile_view(int n, int p, int m, int gw) {
+// ci_comp: the batch's inequality block arrives column-compressed (mgqp_batch::CI_val / CI_row) and STAYS that way in
+// shared memory -- m values and m int rows per QP instead of the dense n x m block, which for the reference's shipped
+// shapes (n = 14, m = 28) is a third of a QP's footprint: more warps per SM.
+MGQP_HOST inline TileView make_tile_view(int n, int p, int m, int gw, int ci_comp = 0) {
   TileView tv;
   tv.n = n; tv.p = p; tv.m = m;
   tv.qpw = 32 / gw;
+  tv.ci_comp = ci_comp;
+  tv.cisz = ci_comp ? m + (m + 1) / 2 : n * m;
   int o = 0;
   // every field offset is kept even (16-byte aligned) so that a whole tile of a field can be
   // fetched with one bulk copy
@@ -61,7 +67,7 @@ MGQP_HOST inline TileView make_tile_view(int n, int p, int m, int gw) {
   tv.og0 = o;  o = mgqp_even(o + tv.qpw * n);
   tv.oCE = o;  o = mgqp_even(o + tv.qpw * n * p);
   tv.oce0 = o; o = mgqp_even(o + tv.qpw * p);
-  tv.oCI = o;  o = mgqp_even(o + tv.qpw * n * m);
+  tv.oCI = o;  o = mgqp_even(o + tv.qpw * tv.cisz);
   tv.oci0 = o; o = mgqp_even(o + tv.qpw * m);
   tv.oWork = o;
   tv.ldJ = n | 1;  // odd leading dimension: row-strided 64-bit accesses stay bank-conflict free
@@ -153,7 +159,9 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   const double* sg0 = ws + tv.og0 + g * n;
   const double* sCE = ws + tv.oCE + g * n * p;
   const double* sce0 = ws + tv.oce0 + g * p;
-  const double* sCI = ws + tv.oCI + g * n * m;
+  const double* sCI = ws + tv.oCI + g * tv.cisz;  // dense: [n][m]; compressed: value[m] | row[m] (int)
+  const bool comp = tv.ci_comp != 0;
+  const int* sCIr = reinterpret_cast<const int*>(sCI + m);
   const double* sci0 = ws + tv.oci0 + g * m;
   double* wk = ws + tv.oWork + g * tv.wstride;
   double* sJ = wk + tv.wJ;
@@ -165,6 +173,14 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
   double* sgc = wk + tv.wgc;
   double* sgs = wk + tv.wgs;
   double* sgx = wk + tv.wgx;
+  // Column i of a compressed block times x, as the reference's n-term sum from +0.0 comes out: the zero terms leave
+  // a finite running sum alone (and turn -0.0 into +0.0), but 0 * inf = NaN -- so a non-finite x entry anywhere
+  // but in the column's own row poisons the sum.  nbad / kbad: number of non-finite entries of x, index of the first.
+  auto comp_dot = [&](int i, int nbad, int kbad) -> double {
+    const int k = sCIr[i];
+    const double prod = d_add(0.0, d_mul(sCI[i], sx[k]));
+    return (nbad == 0 || (nbad == 1 && k == kbad)) ? prod : d_sub(INF, INF);
+  };
 
   // ordered (ascending-index) sum of one value per lane, replicated to the whole group
   auto osum = [&](double v) -> double {
@@ -605,14 +621,25 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       }
       double best = ss, psi = 0.0;
       int bidx = NONE;
+      int nbad = 0, kbad = 0;
+      if (comp) {
+        const unsigned bal = wp_ballot(in_n && !(d_abs(xv) < INF));
+        const unsigned bits = (GW == 32) ? bal : ((bal >> (g * GW)) & ((1u << (GW & 31)) - 1u));
+        nbad = i_popc(bits);
+        kbad = bits ? (wp_ffs(bits) - 1) : 0;
+      }
       MGQP_UNROLL1
       for (int k = 0; k < nk; k++) {
         const int i = li + (k << LOGG);
         if (i < m) {
           double sum = 0.0;
-          const double* pc = sCI + i;
-          MGQP_UNROLL_HOT
-          for (int j = 0; j < n; j++, pc += m) sum = mad<FMA>(*pc, sx[j], sum);
+          if (comp) {
+            sum = comp_dot(i, nbad, kbad);
+          } else {
+            const double* pc = sCI + i;
+            MGQP_UNROLL_HOT
+            for (int j = 0; j < n; j++, pc += m) sum = mad<FMA>(*pc, sx[j], sum);
+          }
           sum = d_add(sum, sci0[i]);
           if (sum < 0.0) psi = d_add(psi, sum);
           if (sum < best && !((act_mask >> k) & 1u) && ((excl_mask >> k) & 1u)) {
@@ -639,8 +666,12 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
             MGQP_UNROLL1
             for (int i = 0; i < m; i++) {
               double sum = 0.0;
-              MGQP_UNROLL1
-              for (int j = 0; j < n; j++) sum = mad<FMA>(sCI[j * m + i], sx[j], sum);
+              if (comp) {
+                sum = comp_dot(i, nbad, kbad);
+              } else {
+                MGQP_UNROLL1
+                for (int j = 0; j < n; j++) sum = mad<FMA>(sCI[j * m + i], sx[j], sum);
+              }
               sum = d_add(sum, sci0[i]);
               psi = d_add(psi, (sum < 0.0) ? sum : 0.0);
             }
@@ -679,7 +710,14 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
       }
     }
     if (!wp_any(!done)) break;
-    direction(sCI + ip, m);
+    if (comp) {
+      // the pending column as a vector, in r's place (free until update_r rewrites it at the end of direction)
+      if (in_n) sr[li] = (m > 0 && li == sCIr[ip]) ? sCI[ip] : 0.0;
+      wp_sync();
+      direction(sr, 1);
+    } else {
+      direction(sCI + ip, m);
+    }
 
     // ---------------- step 2b: step lengths
     double ratio = INF;
@@ -789,7 +827,8 @@ MGQP_DEV void gi_solve_tile(const TileView& tv, double* ws, int cnt, int max_ite
     if (in_n) sx[li] = xv;
     if (wp_any(partial)) {
       // s[ip] = CI[:,ip].x + ci0[ip] with the new x
-      const double v = osum(d_mul(in_n ? sCI[li * m + ip] : 0.0, xv));
+      const double cip = comp ? ((in_n && li == sCIr[ip]) ? sCI[ip] : 0.0) : (in_n ? sCI[li * m + ip] : 0.0);
+      const double v = osum(d_mul(cip, xv));
       if (partial) s_ip = d_add(v, sci0[ip]);
     }
     wp_sync();

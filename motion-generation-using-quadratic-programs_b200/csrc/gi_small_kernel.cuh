@@ -120,7 +120,20 @@ __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant_
     }
     // fields that cannot go through TMA (odd alignment, broadcast or padded strides, tail tile):
     // plain coalesced loads; groups beyond the tail replicate the tile's first QP
-    if (P.ci_val && P.size[4] > 0) {
+    if (P.ci_val && P.size[4] > 0 && P.tv.ci_comp) {
+      // column-compressed constraints stay compressed: m values and m rows (int) per QP
+      const int n = P.tv.n, m = P.tv.m, cs = P.tv.cisz;
+      double* ci = ws + P.off[4];
+#pragma unroll 1
+      for (int idx = lane; idx < QPW * m; idx += 32) {
+        const int q = idx / m, i = idx - q * m;
+        const long long qq = q0 + (q < cnt ? q : 0);
+        unsigned r = __ldg(P.ci_row + qq * P.s_ci_row + i);
+        r = r < (unsigned)n ? r : (unsigned)(n - 1);
+        ci[q * cs + i] = __ldg(P.ci_val + qq * P.s_ci_val + i);
+        reinterpret_cast<int*>(ci + q * cs + m)[i] = (int)r;
+      }
+    } else if (P.ci_val && P.size[4] > 0) {
       // column-compressed constraints: rebuild the dense n x m block in shared memory (zeros, then one
       // coefficient per column).  The kernel's sums start from +0.0, so a +0.0 where the caller's block
       // had -0.0 cannot change any result.

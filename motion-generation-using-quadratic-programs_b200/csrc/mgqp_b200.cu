@@ -143,7 +143,10 @@ struct Plan {
 // SM shared-memory budget used for planning when no device is queried (B200: 227 KB opt-in).
 constexpr int kSmemBudget = 227 * 1024;
 
-Plan make_plan(int n, int p, int m, int smem_optin) {
+#ifndef MGQP_SMALL_CI_COMP
+#define MGQP_SMALL_CI_COMP 1   // column-compressed CI stays compressed in the group kernel's shared memory
+#endif
+Plan make_plan(int n, int p, int m, int smem_optin, int ci_comp = 0) {
   Plan pl;
   if (n < 1 || p < 0 || m < 0) return pl;
   int gw = n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 0;
@@ -153,7 +156,7 @@ Plan make_plan(int n, int p, int m, int smem_optin) {
     return pl;
   }
   for (;; gw *= 2) {
-    TileView tv = make_tile_view(n, p, m, gw);
+    TileView tv = make_tile_view(n, p, m, gw, ci_comp);
     const long long per_warp = (long long)tv.total * 8;
     // one CTA per SM unless warps are small; leave the 1 KB/CTA the driver reserves
     int warps = (int)((smem_optin - 1024 - 256) / per_warp);
@@ -417,7 +420,9 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const un
     }
   }
 
-  const Plan pl = (d->flags & MGQP_FLAG_CTA_KERNEL) ? Plan() : make_plan(d->n, d->p, d->m, ctx->smem_optin);
+  const Plan pl = (d->flags & MGQP_FLAG_CTA_KERNEL)
+                      ? Plan()
+                      : make_plan(d->n, d->p, d->m, ctx->smem_optin, (MGQP_SMALL_CI_COMP && d->CI_val && d->m > 0) ? 1 : 0);
   if (pl.gw < 0) {
     if (d->CI_val && d->m)
       return fail(MGQP_ERR_UNSUPPORTED_SHAPE,

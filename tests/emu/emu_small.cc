@@ -74,6 +74,46 @@ extern "C" int emu_solve_batch(int n, int p, int m, long long batch, const doubl
   return 0;
 }
 
+// The same with the inequality block kept column-compressed in the (emulated) shared memory, as the kernel keeps a
+// batch that arrives as mgqp_batch::CI_val / CI_row: CIv [batch][m] values, CIr [batch][m] rows.
+extern "C" int emu_solve_batch_comp(int n, int p, int m, long long batch, const double* G, const double* g0,
+                                    const double* CE, const double* ce0, const double* CIv, const unsigned char* CIr,
+                                    const double* ci0, double* x, double* f, int* status, int* iq, int* A, int* iters,
+                                    int max_iter, int gw, int fma) {
+  if (n > gw || m > 32 * gw) return -2;
+  const TileView tv = make_tile_view(n, p, m, gw, 1);
+  const int qpw = tv.qpw;
+  const long long tiles = (batch + qpw - 1) / qpw;
+  if (max_iter <= 0) max_iter = 100 + 10 * (p + m);
+  std::vector<double> ws(tv.total);
+  for (long long t = 0; t < tiles; t++) {
+    const long long q0 = t * qpw;
+    const int cnt = (int)((batch - q0) < qpw ? (batch - q0) : qpw);
+    for (int g = 0; g < qpw; g++) {
+      const long long q = q0 + (g < cnt ? g : 0);
+      memcpy(&ws[tv.oG + g * n * n], G + q * n * n, sizeof(double) * n * n);
+      memcpy(&ws[tv.og0 + g * n], g0 + q * n, sizeof(double) * n);
+      memcpy(&ws[tv.oCE + g * n * p], CE + q * n * p, sizeof(double) * n * p);
+      memcpy(&ws[tv.oce0 + g * p], ce0 + q * p, sizeof(double) * p);
+      double* ci = &ws[tv.oCI + g * tv.cisz];
+      for (int i = 0; i < m; i++) {
+        ci[i] = CIv[q * m + i];
+        unsigned r = CIr[q * m + i];
+        reinterpret_cast<int*>(ci + m)[i] = (int)(r < (unsigned)n ? r : (unsigned)(n - 1));
+      }
+      memcpy(&ws[tv.oci0 + g * m], ci0 + q * m, sizeof(double) * m);
+    }
+    Job j;
+    j.tv = tv; j.ws = ws.data(); j.cnt = cnt; j.max_iter = max_iter; j.gw = gw; j.fma = fma;
+    j.out.x = x + q0 * n; j.out.f = f + q0; j.out.status = status + q0;
+    j.out.iq = iq ? iq + q0 : nullptr;
+    j.out.A = A ? A + q0 * (p + m) : nullptr;
+    j.out.iters = iters ? iters + q0 : nullptr;
+    emu_run_warp(lane_body, &j);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------ lane-per-QP solver (gi_lane.cuh)
 #include "../../motion-generation-using-quadratic-programs_b200/csrc/gi_lane.cuh"
 

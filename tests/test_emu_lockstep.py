@@ -97,3 +97,56 @@ def test_fast_math_mode_within_tolerance(emu_lib, restatement):
     b = workloads.make("C2", 301)
     got = emu_solve(emu_lib, b, 8, fma=1)
     assert_parity(got, _oracle(restatement, b), "C2/fast")
+
+
+def _emu_solve_comp(lib, b, gw, fma=0):
+    """The group kernel's solver with the inequality block kept column-compressed in shared memory (values | rows)."""
+    import ctypes as C
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    B, n, p, m = b.batch, b.n, b.p, b.m
+    nz = b.CI != 0
+    assert (nz.sum(axis=1) <= 1).all()
+    row = nz.argmax(axis=1).astype(np.uint8)
+    val = np.take_along_axis(b.CI, row[:, None, :].astype(np.int64), axis=1)[:, 0, :]
+    val = np.where(nz.any(axis=1), val, 0.0)
+    G, g0, CE, ce0, _, ci0 = [np.ascontiguousarray(a, dtype=np.float64) for a in b.fields()]
+    val = np.ascontiguousarray(val)
+    x = np.zeros((B, n)); f = np.zeros(B)
+    st = np.zeros(B, np.int32); iq = np.zeros(B, np.int32); A = np.zeros((B, p + m), np.int32); it = np.zeros(B, np.int32)
+    lib.emu_solve_batch_comp.restype = C.c_int
+    rc = lib.emu_solve_batch_comp(C.c_int(n), C.c_int(p), C.c_int(m), C.c_longlong(B), G.ctypes.data_as(dp),
+                                  g0.ctypes.data_as(dp), CE.ctypes.data_as(dp), ce0.ctypes.data_as(dp),
+                                  val.ctypes.data_as(dp), row.ctypes.data_as(C.POINTER(C.c_ubyte)), ci0.ctypes.data_as(dp),
+                                  x.ctypes.data_as(dp), f.ctypes.data_as(dp), *[a.ctypes.data_as(ip) for a in (st, iq, A, it)],
+                                  C.c_int(0), C.c_int(gw), C.c_int(fma))
+    assert rc == 0
+    return dict(x=x, f=f, status=st, iq=iq, A=A, iters=it)
+
+
+@pytest.mark.parametrize("name,B,gw", [("S0", 301, 16), ("S2", 301, 16), ("C2", 203, 8), ("C5", 203, 8), ("C5D", 150, 16)])
+def test_compressed_constraints_stay_compressed_in_shared_memory(emu_lib, restatement, name, B, gw):
+    b = workloads.make(name, B)
+    if name in ("S0", "S2"):
+        b.ci0[::7, 3] = -0.3                 # bounds that bite: iterations past the equality phase
+        b.ci0[::7, 3 + 14] = -0.3            # ... and contradict each other (infeasible verdicts)
+        b.ci0[1::7, 5] = -0.05
+        b.g0[2::11] = np.random.default_rng(1).standard_normal((len(b.g0[2::11]), b.n))
+    b.CI[3::13, :, 1] = 0.0                  # an empty column
+    b.CI[4::13][b.CI[4::13] == 0] = -0.0     # negative zeros stay zeros
+    b.CI[5::13, :, 2] *= 0.37                # a non-unit coefficient
+    ref = _oracle(restatement, b)
+    assert ref["iters"].max() > 1
+    assert_bit_identical(_emu_solve_comp(emu_lib, b, gw), ref, name + " compressed")
+
+
+def test_compressed_constraints_with_non_finite_iterates(emu_lib, restatement):
+    """0 * inf = NaN: a non-finite x entry poisons every column's sum except through the column's own row."""
+    b = workloads.make("S2", 120)
+    b.g0[0::6, 2] = np.inf
+    b.g0[1::6, 4] = -np.inf
+    b.g0[2::6, 1] = np.nan
+    b.g0[3::6, [0, 7]] = np.inf
+    b.ce0[4::6, 0] = np.inf
+    ref = _oracle(restatement, b)
+    assert_bit_identical(_emu_solve_comp(emu_lib, b, 16), ref, "S2 compressed, non-finite")
+    assert_bit_identical(emu_solve(emu_lib, b, 16), ref, "S2 dense, non-finite")
