@@ -15,15 +15,21 @@ ap.add_argument("--workload", default="C2")
 ap.add_argument("--batch", type=int, default=200000)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--compressed", action="store_true", help="hand CI over as (value, row) columns")
 a = ap.parse_args()
 b = workloads.make(a.workload, a.batch)
 t = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in b.fields()]
-out = mgqp_b200.solve_quadprog_batched(*t, flags=a.flags, want_active_set=True)
+kw = {}
+if a.compressed:
+    val, row = mgqp_b200.pack_bound_columns(b.CI)
+    kw = dict(CI_val=torch.from_numpy(val).cuda(), CI_row=torch.from_numpy(row).cuda())
+    t[4] = None
+out = mgqp_b200.solve_quadprog_batched(*t, flags=a.flags, want_active_set=True, **kw)
 torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record()
 for _ in range(a.reps):
-    mgqp_b200.solve_quadprog_batched(*t, flags=a.flags, out=out)
+    mgqp_b200.solve_quadprog_batched(*t, flags=a.flags, out=out, **kw)
 ev1.record()
 torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / a.reps
