@@ -30,6 +30,8 @@ struct SmallParams {
   long long s_ci_val, s_ci_row;
   const unsigned long long* batch_dev;  // if set: the number of QPs lives on the device (<= batch)
   int fuse_retry;        // TileOut::fuse_retry
+  const int* gate;       // if set: run only if (*gate != 0) == (gate_want != 0) (the launcher's classification verdict)
+  int gate_want;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -69,6 +71,7 @@ template <int GW, bool FMA>
 __global__ void __launch_bounds__(512, 1) gi_small_kernel(const __grid_constant__ SmallParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int QPW = 32 / GW;
+  if (P.gate && (__ldg(P.gate) != 0) != (P.gate_want != 0)) return;  // the other layout serves this batch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw) + warp;

@@ -55,6 +55,9 @@ constexpr int kMaxDev = 16;
 // internal flag bit (never part of the ABI): the first solve of a retry call may answer the retry itself where
 // that is exact (gi_small.cuh, TileOut::fuse_retry)
 constexpr int kFlagFuseRetry = 1 << 30;
+// internal: the caller knows its dense inequality block is not made of bound columns (the cascade's projected
+// limits): skip the classification pre-pass of the group kernel
+constexpr int kFlagDenseCI = 1 << 29;
 // Work-queue heads, one slot per launch, reused round robin: two launches only ever share a slot if
 // more than kTicketRing launches of this library are in flight on one device at the same time.
 constexpr int kTicketRing = 4096;
@@ -348,6 +351,61 @@ int launch_large(DeviceCtx* ctx, const LargePlan& lp, LargeParams& P, cudaStream
 }
 
 // the caller's current device is put back when an entry point returns
+// tuning / A-B knob: MGQP_SMALL_CLASSIFY=0 keeps a dense block dense (the behaviour before the pre-pass existed)
+bool classify_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("MGQP_SMALL_CLASSIFY");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// Device-side counterpart of mgqp_pack_bound_columns (host_pack.cc) for a DENSE inequality block handed to the
+// device-resident entry point: one thread per (QP, column) walks the column's n coefficients (+-0.0 are the zeros, NaN
+// counts as a nonzero) and writes the (value, row) pair -- (+0.0, row 0) for an all-zero column -- or raises *mixed
+// if the column has a second nonzero.  The group kernel is then launched twice, gated on *mixed: the compressed layout
+// (more warps per SM) runs if every column of the batch was a bound, the dense layout otherwise; the other launch
+// exits at once.  No host synchronisation: the call stays asynchronous and graph-capturable.
+__global__ void __launch_bounds__(256) bound_columns_kernel(long long total, int n, int m, const double* __restrict__ CI,
+                                                            long long sCI, double* __restrict__ val,
+                                                            unsigned char* __restrict__ row, int* mixed) {
+  // One look at the verdict per block and one write per block that finds a second nonzero: every thread polling or
+  // raising the same word cost 0.3 ms per launch whatever the batch (`r06g`).
+  __shared__ int stop;
+  if (threadIdx.x == 0) stop = *reinterpret_cast<volatile int*>(mixed);
+  __syncthreads();
+  if (stop) return;  // verdict known: the compressed launch will not run
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  double v = 0.0;
+  int r = 0, cnt = 0;
+  if (e < total) {
+    const long long q = e / m;
+    const int i = (int)(e - q * m);
+    const double* c = CI + q * sCI + i;
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {  // four loads in flight per thread
+      const double a0 = __ldg(c + (long long)j * m), a1 = __ldg(c + (long long)(j + 1) * m);
+      const double a2 = __ldg(c + (long long)(j + 2) * m), a3 = __ldg(c + (long long)(j + 3) * m);
+      if ((__double_as_longlong(a0) & 0x7fffffffffffffffll) != 0) { v = a0; r = j; cnt++; }
+      if ((__double_as_longlong(a1) & 0x7fffffffffffffffll) != 0) { v = a1; r = j + 1; cnt++; }
+      if ((__double_as_longlong(a2) & 0x7fffffffffffffffll) != 0) { v = a2; r = j + 2; cnt++; }
+      if ((__double_as_longlong(a3) & 0x7fffffffffffffffll) != 0) { v = a3; r = j + 3; cnt++; }
+    }
+    for (; j < n; j++) {
+      const double a = __ldg(c + (long long)j * m);
+      if ((__double_as_longlong(a) & 0x7fffffffffffffffll) != 0) { v = a; r = j; cnt++; }
+    }
+  }
+  if (__syncthreads_or(cnt > 1)) {
+    if (threadIdx.x == 0) *mixed = 1;
+    return;
+  }
+  if (e < total) {
+    val[e] = v;
+    row[e] = (unsigned char)r;
+  }
+}
+
 struct DeviceGuard {
   int prev = -1;
   DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
@@ -373,7 +431,8 @@ int validate(const mgqp_batch* d) {
   return MGQP_OK;
 }
 
-int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const unsigned long long* batch_dev = nullptr) {
+int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const unsigned long long* batch_dev = nullptr,
+                      const int* gate = nullptr, int gate_want = 0) {
   int rc = validate(d);
   if (rc) return rc;
   if (d->batch == 0) return MGQP_OK;
@@ -423,6 +482,40 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const un
   const Plan pl = (d->flags & MGQP_FLAG_CTA_KERNEL)
                       ? Plan()
                       : make_plan(d->n, d->p, d->m, ctx->smem_optin, (MGQP_SMALL_CI_COMP && d->CI_val && d->m > 0) ? 1 : 0);
+  // A dense inequality block whose columns may all be bounds (every one the reference builds is): classify it on
+  // the device and let the layout with more resident warps serve the batch if it qualifies.
+  if (MGQP_SMALL_CI_COMP && pl.gw > 0 && !gate && !batch_dev && d->CI && !d->CI_val && d->m > 0 && d->n <= 255 &&
+      !(d->flags & (kFlagDenseCI | MGQP_FLAG_NO_HOST_PACK)) && classify_enabled()) {
+    const Plan pc = make_plan(d->n, d->p, d->m, ctx->smem_optin, 1);
+    // more warps only pay once the batch outgrows one resident wave of the dense layout
+    if (pc.gw == pl.gw && pc.warps > pl.warps && d->batch > (long long)ctx->sms * pl.warps * pl.tv.qpw) {
+      const long long cnt = d->sCI ? d->batch : 1, m = d->m;
+      const size_t val_bytes = (size_t)(cnt * m) * 8, row_bytes = ((size_t)(cnt * m) + 15) & ~(size_t)15;
+      void* buf = nullptr;
+      CU(cudaMallocFromPoolAsync(&buf, val_bytes + row_bytes + 16, ctx->pool, st));
+      double* val = static_cast<double*>(buf);
+      unsigned char* row = static_cast<unsigned char*>(buf) + val_bytes;
+      int* mixed = reinterpret_cast<int*>(row + row_bytes);
+      int rc2 = MGQP_OK;
+      cudaError_t e = cudaMemsetAsync(mixed, 0, sizeof(int), st);
+      if (e == cudaSuccess) {
+        const long long blocks = (cnt * m + 255) / 256;
+        bound_columns_kernel<<<(unsigned)blocks, 256, 0, st>>>(cnt * m, d->n, d->m, d->CI, d->sCI, val, row, mixed);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+      }
+      if (e != cudaSuccess) rc2 = fail(MGQP_ERR_CUDA, "bound_columns_kernel: %s", cudaGetErrorString(e));
+      if (!rc2) {
+        mgqp_batch c = *d;
+        c.CI_val = val; c.CI_row = row;
+        c.sCIv = d->sCI ? m : 0; c.sCIr = d->sCI ? m : 0;
+        rc2 = solve_device_once(&c, device, st, nullptr, mixed, 0);
+      }
+      if (!rc2) rc2 = solve_device_once(d, device, st, nullptr, mixed, 1);
+      cudaFreeAsync(buf, st);
+      return rc2;
+    }
+  }
   if (pl.gw < 0) {
     if (d->CI_val && d->m)
       return fail(MGQP_ERR_UNSUPPORTED_SHAPE,
@@ -491,6 +584,8 @@ int solve_device_once(const mgqp_batch* d, int device, cudaStream_t st, const un
   P.ticket = ticket;
   P.batch_dev = batch_dev;
   P.fuse_retry = (d->flags & kFlagFuseRetry) ? 1 : 0;
+  P.gate = gate;
+  P.gate_want = gate_want;
   const int gi = pl.gw == 8 ? 0 : pl.gw == 16 ? 1 : 2;
   if (pl.gw == 8) return fast ? launch_small<8, true>(ctx, pl, P, st, gi, 1) : launch_small<8, false>(ctx, pl, P, st, gi, 0);
   if (pl.gw == 16) return fast ? launch_small<16, true>(ctx, pl, P, st, gi, 1) : launch_small<16, false>(ctx, pl, P, st, gi, 0);
@@ -936,7 +1031,7 @@ int cascade_device(const mgqp_scenarios* s, int device, cudaStream_t st) {
     l2.G = cG; l2.g0 = cg0; l2.CE = P.CE2; l2.ce0 = P.ce02; l2.CI = P.CI2; l2.ci0 = P.ci0;
     l2.sG = 0; l2.sg0 = 0; l2.sCE = 14; l2.sce0 = 1; l2.sCI = 392; l2.sci0 = 28;
     l2.x = x2; l2.f = f2; l2.status = st2;
-    l2.flags = MGQP_FLAG_RETRY_WITHOUT_CI;
+    l2.flags = MGQP_FLAG_RETRY_WITHOUT_CI | kFlagDenseCI;  // limitsMatrix * Z: dense rows of rank 4
     if ((rc = solve_device(&l2, device, st))) return rc;
     cascade_finish_kernel<<<blocks, 128, 0, st>>>(P);
     g_launches.fetch_add(1);

@@ -332,6 +332,44 @@ def test_column_compressed_device_input(gpu, restatement):
         gpu.solve_quadprog_batched(*t, CI_val=val, CI_row=row)
 
 
+def test_dense_block_classified_on_the_device(gpu, restatement):
+    """A dense inequality block handed to the device-resident entry point: the launcher classifies it on the device
+    (bound_columns_kernel) and the group kernel runs with the compressed layout if every column of the batch is a
+    bound, with the dense one otherwise.  Batches above one resident wave (148 SMs x 11 warps x 2 QPs) take that path."""
+    import torch
+    for name, B in (("S0", 5003), ("S2", 5001)):
+        b = workloads.make(name, B)
+        b.CI[2::31][b.CI[2::31] == 0] = -0.0      # -0.0 is a zero
+        b.CI[3::37, :, 6] = 0.0                    # an all-zero column
+        b.CI[5::41, np.flatnonzero(b.CI[0, :, 3])[0], 3] = np.nan   # NaN where the column's nonzero is
+        b.ci0[7::53, 4] = np.nan
+        b.g0[11::59, 1] = np.inf
+        assert gpu.pack_bound_columns(b.CI) is not None
+        assert_bit_identical(_solve(gpu, b), _oracle(restatement, b), name + " all bounds")
+        # one QP anywhere in the batch with a second coefficient in a column: the whole batch runs dense
+        for q in (0, B // 2, B - 1):
+            c = workloads.make(name, B)
+            c.CI[q, (np.flatnonzero(c.CI[q, :, 5])[0] + 1) % c.n, 5] = 0.25
+            assert gpu.pack_bound_columns(c.CI) is None
+            assert_bit_identical(_solve(gpu, c), _oracle(restatement, c), f"{name} mixed at {q}")
+        # one block for the whole batch (leading dimension 1)
+        t = _dev(b)
+        r = gpu.solve_quadprog_batched(t[0], t[1], t[2], t[3], t[4][:1], t[5], want_active_set=True)
+        torch.cuda.synchronize()
+        b.CI[:] = b.CI[:1]
+        assert_bit_identical({k: v.cpu().numpy() for k, v in r._asdict().items()}, _oracle(restatement, b), name + " one CI")
+        # with the retry policy on top (the verdict bit and the second solve see the same first answers)
+        b = workloads.make(name, B)
+        b.ci0[::9, 3] = -50.0
+        got = _solve(gpu, b, flags=64)
+        val, row = gpu.pack_bound_columns(b.CI)
+        t = _dev(b)
+        r = gpu.solve_quadprog_batched(t[0], t[1], t[2], t[3], None, t[5], want_active_set=True, flags=64,
+                                       CI_val=torch.from_numpy(val).cuda(), CI_row=torch.from_numpy(row).cuda())
+        torch.cuda.synchronize()
+        assert_bit_identical(got, {k: v.cpu().numpy() for k, v in r._asdict().items()}, name + " retry")
+
+
 def test_host_pipeline_compressed_transport(gpu, restatement):
     """The host-buffer entry point ships CI column-compressed chunk by chunk when it can, dense when it
     cannot; either way the results are those of the oracle, bit for bit."""
