@@ -69,8 +69,10 @@ enum {
   MGQP_FLAG_GROUP_KERNEL = 8,
   /* Always use the CTA-per-QP kernel (the one that serves n > 32). */
   MGQP_FLAG_CTA_KERNEL = 16,
-  /* Host-buffer entry points only: ship CI to the device as it is (dense) instead of in the
-   * column-compressed transport form described at mgqp_batch::CI_val. */
+  /* Host-buffer entry points: ship CI to the device as it is (dense) instead of in the
+   * column-compressed transport form described at mgqp_batch::CI_val.  Device-resident entry
+   * point: do not classify a dense CI on the device either (n in 9..32: the lane-group kernel
+   * otherwise keeps a block made of bound columns compressed in shared memory; same answers). */
   MGQP_FLAG_NO_HOST_PACK = 32,
   /* The reference adapter's policy for an infeasible answer (solveNextStep, src/mgqp.cpp:717-735,
    * TRY_TO_CONVERGE): every QP whose cost comes back NaN or +inf is solved again WITHOUT its
